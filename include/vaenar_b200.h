@@ -1,0 +1,145 @@
+/* vaenar_b200.h -- C ABI of libvaenar_sm100.so: the B200-native (sm_100a) implementation of the
+ * VAENAR-TTS non-autoregressive mel-synthesis hot path.
+ *
+ * The reference (thuhcsi/VAENAR-TTS) has no FFI layer: the operator boundary of the path is the Keras
+ * object API of models/models.py:9-226 as consumed by train.py:120-179 and inference.py:55-72,125-143.
+ * Each entry point below replaces one of those Python call sites (cited per function); the Python mirror
+ * (vaenar_tts_b200/model.py) binds them with ctypes and re-exposes the reference's names.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative code on error; vaenar_last_error() gives the text;
+ *   - the CALLER owns all memory: parameters (one flat fp32 buffer laid out by the manifest below), the
+ *     packed fp16 weight arena, the workspace, all inputs and outputs.  Nothing is allocated or freed here
+ *     and no call synchronises the host with the device;
+ *   - all pointers are device pointers unless stated; tensors are row-major [batch, time, channel] fp32,
+ *     token ids and lengths int32; `stream` is a cudaStream_t passed as void*;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef VAENAR_B200_H_
+#define VAENAR_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vaenar_model* vaenar_handle_t;
+
+/* Mirrors the values models/models.py:16-65 reads from configs/hparams.py:233-348 (LJHPS) / :351-474. */
+typedef struct vaenar_hparams {
+  int32_t vocab_size, embd_dim, enc_n_conv, enc_hidden, enc_conv_kernel, enc_n_blk, enc_att_dim, enc_heads, enc_ffn;
+  int32_t dec_nblk, dec_att_dim, dec_heads, dec_ffn, post_n_conv, post_filters, post_kernel;
+  int32_t posterior_pre_hidden, posterior_nblk, posterior_att_dim, posterior_heads, posterior_ffn;
+  int32_t prior_n_blk, prior_n_tblk, prior_att_dim, prior_heads, prior_ffn;
+  int32_t latent_dim, out_dim, max_reduction_factor, final_reduction_factor;
+  float mel_text_len_ratio;
+} vaenar_hparams_t;
+
+const char* vaenar_last_error(void);
+int vaenar_abi_version(void);
+
+/* VAENAR.__init__ (models/models.py:10-65): builds the parameter manifest; allocates no device memory. */
+int vaenar_create(const vaenar_hparams_t* hps, vaenar_handle_t* out);
+int vaenar_destroy(vaenar_handle_t h);
+
+/* Parameter manifest: model.trainable_variables + BN moving stats (train.py:136-137), attribute-path
+ * names of SURVEY.md Appendix B, Keras layouts (Dense [in,out], Conv1D [k,in,out]).  All parameters live
+ * in ONE flat fp32 buffer; offsets are in floats. */
+int vaenar_num_params(vaenar_handle_t h);
+const char* vaenar_param_name(vaenar_handle_t h, int i);
+int vaenar_param_ndim(vaenar_handle_t h, int i);
+int64_t vaenar_param_dim(vaenar_handle_t h, int i, int d);
+int64_t vaenar_param_offset(vaenar_handle_t h, int i);
+int vaenar_param_trainable(vaenar_handle_t h, int i);
+int64_t vaenar_param_floats(vaenar_handle_t h);
+
+int64_t vaenar_packed_bytes(vaenar_handle_t h);
+int64_t vaenar_workspace_bytes(vaenar_handle_t h, int B, int T_text, int T_z, int rf);
+
+/* Re-layout of the fp32 master weights into the kernel operand formats (fp16 [out,in] K-major matrices,
+ * folded inference BatchNorm, ActNorm(+)InvertibleLinear folded 128x128 maps, float64 log|det W| and the
+ * fp32 inverse of modules/flow.py:126-144).  Call after every change of the parameters. */
+int vaenar_pack_weights(vaenar_handle_t h, const float* params, void* packed, void* stream);
+
+/* TransformerEncoder.call (modules/encoder.py:79-93), training=False: text_embd [B, T_text, embd]. */
+int vaenar_text_encoder_fwd(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
+                            const int32_t* texts, const int32_t* text_lengths, int B, int T_text, float pos_step,
+                            float* text_embd, void* stream);
+
+/* DenseLengthPredictor.call (modules/length_predictor.py:35-42): predicted lengths [B] (float). */
+int vaenar_length_predictor_fwd(vaenar_handle_t h, const float* params, const float* text_embd,
+                                const int32_t* text_lengths, int B, int T_text, float* pred_lengths, void* stream);
+
+/* TransformerPrior.sample (modules/prior.py:154-169).  z_io holds the initial noise epsilon
+ * [B, T_z, latent] on entry (already scaled by the temperature) and the sampled latents on return;
+ * logp [B] receives the log-density. */
+int vaenar_prior_sample(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
+                        const float* text_embd, const int32_t* text_lengths, const int32_t* z_lengths, int B,
+                        int T_text, int T_z, float* z_io, float* logp, void* stream);
+
+/* TransformerPrior.log_probability (modules/prior.py:119-152): logp [B] of given latents z [B,T_z,latent]
+ * (z is not modified). */
+int vaenar_prior_log_probability(vaenar_handle_t h, const float* params, const void* packed, void* ws,
+                                 int64_t ws_bytes, const float* z, const float* text_embd,
+                                 const int32_t* text_lengths, const int32_t* z_lengths, int B, int T_text, int T_z,
+                                 float* logp, void* stream);
+
+/* TransformerPosterior.call + reparameterize + log_probability (modules/posterior.py:20-72,115-130) as
+ * wired by VAENAR.call (models/models.py:123,136-144; the (logvar, mu) name swap of :136 is honoured):
+ * mels [B,T_mel,80], eps [B,T_z,latent] -> z [B,T_z,latent], logq [B].  training=False (no dropout). */
+int vaenar_posterior_fwd(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
+                         const float* mels, const float* text_embd, const int32_t* text_lengths,
+                         const int32_t* z_lengths, const float* eps, int B, int T_text, int T_mel, int T_z, int rf,
+                         float* z, float* logq, void* stream);
+
+/* TransformerDecoder.call (modules/decoder.py:181-199), training=False: initial / final mel
+ * [B, T_z*rf, 80]; alignments (nullable) [dec_nblk, B, heads, T_z, T_text]. */
+int vaenar_decoder_fwd(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
+                       const float* z, const float* text_embd, const int32_t* z_lengths,
+                       const int32_t* text_lengths, int B, int T_text, int T_z, int rf, float* initial_mel,
+                       float* mel, float* alignments, void* stream);
+
+/* VAENAR.inference (models/models.py:199-210): encoder -> prior.sample -> decoder in one call (one CUDA
+ * graph capturable launch sequence).  z_io: epsilon in / latents out. */
+int vaenar_inference(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
+                     const int32_t* texts, const int32_t* text_lengths, const int32_t* z_lengths, int B, int T_text,
+                     int T_z, int rf, float* z_io, float* text_embd, float* mel, float* alignments, float* logp,
+                     void* stream);
+
+/* VAENAR.call forward (models/models.py:105-197), training=False, n_sample=1, per-example losses:
+ * l2 [B], kl [B], length_loss [B]; decoded mel [B, T_mel, 80] (cropped to T_mel). */
+int vaenar_elbo_fwd(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
+                    const int32_t* texts, const float* mels, const int32_t* mel_lengths,
+                    const int32_t* text_lengths, const int32_t* z_lengths, const float* eps, int B, int T_text,
+                    int T_mel, int T_z, int rf, float* mel_out, float* l2, float* kl, float* length_loss,
+                    float* alignments, void* stream);
+
+/* N(0, stddev) noise from the counter-based generator (replaces tf.random.normal at
+ * modules/posterior.py:35 and modules/prior.py:35). */
+int vaenar_randn(float* out, int64_t n, uint64_t seed, uint64_t stream_id, float stddev, void* stream);
+
+/* Accounting for bench.py: number of kernels this library has launched (captured launches count once at
+ * capture time), and per-launch CUDA-event timing of the tensor-core kernel classes. */
+long vaenar_launch_count(void);
+int vaenar_profile_enable(int on);
+const char* vaenar_profile_report(void);
+
+/* ---- block-level entry points (parity tests of single kernels against the oracle) ---- */
+/* out = act(A[M,K] W[K,N] + bias) (+residual, LayerNorm if ln != 0); A, W fp32 host-layout device buffers;
+ * the call converts operands to fp16 into `ws` and runs the tcgen05 GEMM.  split != 0 uses the split-fp16 path. */
+int vaenar_test_dense(const float* A, const float* W, const float* bias, const float* residual, const float* gamma,
+                      const float* beta, int M, int K, int N, int act, int ln, int split, int block_n, float* out,
+                      void* ws, int64_t ws_bytes, void* stream);
+/* Conv1D k taps 'same' over [B,T,Cin] -> [B,T,Cout] fp32 (bias + act), implicit GEMM on tcgen05. */
+int vaenar_test_conv1d(const float* X, const float* W, const float* bias, int B, int T, int Cin, int Cout, int taps,
+                       int act, int split, float* out, void* ws, int64_t ws_bytes, void* stream);
+/* MultiHeadScaledProductAttention core (modules/attention.py:217-246) on projected q/k/v fp32
+ * [B,Tq,H*64], [B,Tk,H*64]: ctx [B,Tq,H*64] fp32, ali (nullable) [B,H,Tq,Tk]. */
+int vaenar_test_attention(const float* q, const float* k, const float* v, const int32_t* q_len,
+                          const int32_t* k_len, int B, int H, int Tq, int Tk, int causal, float* ctx, float* ali,
+                          void* ws, int64_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAENAR_B200_H_ */

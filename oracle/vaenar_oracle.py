@@ -176,13 +176,39 @@ def cast_params(P: Params, dtype) -> Params:
 # ----------------------------------------------------------------------------------------
 # leaf ops
 # ----------------------------------------------------------------------------------------
+_OPERAND_ROUND = None   # None = exact fp32/fp64.  See emulate_operand_dtype().
+
+
+class emulate_operand_dtype:
+    """Context manager: round the operands of every tensor-core contraction (Dense, Conv1D, QK^T, PV)
+    to ``dtype`` (torch.bfloat16 / torch.float16) while accumulating in the working precision.  Used to
+    predict the error budget of the mixed-precision CUDA path; the flow arithmetic stays exact."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global _OPERAND_ROUND
+        self._prev = _OPERAND_ROUND
+        _OPERAND_ROUND = self.dtype
+        return self
+
+    def __exit__(self, *a):
+        global _OPERAND_ROUND
+        _OPERAND_ROUND = self._prev
+
+
+def _r(x):
+    return x if _OPERAND_ROUND is None else x.to(_OPERAND_ROUND).to(x.dtype)
+
+
 def sequence_mask(lengths: Tensor, maxlen: int, dtype=torch.bool) -> Tensor:
     """tf.sequence_mask: mask[b, t] = t < lengths[b]."""
     return (torch.arange(maxlen)[None, :] < lengths[:, None].long()).to(dtype)
 
 
 def dense(P, name, x, activation=None):
-    y = x @ P[name + ".kernel"]
+    y = _r(x) @ _r(P[name + ".kernel"])
     if (name + ".bias") in P:
         y = y + P[name + ".bias"]
     if activation == "relu":
@@ -219,7 +245,7 @@ def conv1d_bn(P, name, x, activation, training, mask=None, bn_before_act=False, 
     k = w.shape[0]
     pad_l = (k - 1) // 2
     xt = torch.nn.functional.pad(x.transpose(1, 2), (pad_l, k - 1 - pad_l))
-    y = torch.nn.functional.conv1d(xt, w.permute(2, 1, 0), P[name + ".conv1d.bias"]).transpose(1, 2)
+    y = torch.nn.functional.conv1d(_r(xt), _r(w.permute(2, 1, 0)), P[name + ".conv1d.bias"]).transpose(1, 2)
 
     def act(v):
         if activation == "relu":
@@ -249,16 +275,16 @@ def conv1d_bn(P, name, x, activation, training, mask=None, bn_before_act=False, 
 
 def mha(P, name, x, memory, heads, memory_lengths, query_lengths, causality, temperature=1.0):
     """MultiHeadScaledProductAttention.call (modules/attention.py:217-246)."""
-    q = x @ P[name + ".query_layer.kernel"]
-    k = memory @ P[name + ".key_layer.kernel"]
-    v = memory @ P[name + ".value_layer.kernel"]
+    q = _r(x) @ _r(P[name + ".query_layer.kernel"])
+    k = _r(memory) @ _r(P[name + ".key_layer.kernel"])
+    v = _r(memory) @ _r(P[name + ".value_layer.kernel"])
     B, Tq, A = q.shape
     Tk = k.shape[1]
     hd = A // heads
     qh = q.reshape(B, Tq, heads, hd).transpose(1, 2)
     kh = k.reshape(B, Tk, heads, hd).transpose(1, 2)
     vh = v.reshape(B, Tk, heads, hd).transpose(1, 2)
-    logits = qh @ kh.transpose(-1, -2)
+    logits = _r(qh) @ _r(kh).transpose(-1, -2)
     logits = logits / math.sqrt(float(hd))
     logits = logits / temperature
     mmask = sequence_mask(memory_lengths, Tk)[:, None, :].expand(B, Tq, Tk)
@@ -269,7 +295,7 @@ def mha(P, name, x, memory, heads, memory_lengths, query_lengths, causality, tem
     mask = mask[:, None].expand(B, heads, Tq, Tk)
     logits = torch.where(mask, logits, torch.full_like(logits, MASK_FILL))
     ali = torch.softmax(logits, dim=3)
-    ctx = (ali @ vh).transpose(1, 2).reshape(B, Tq, A)
+    ctx = (_r(ali) @ _r(vh)).transpose(1, 2).reshape(B, Tq, A)
     return ctx, ali
 
 

@@ -1,0 +1,91 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol declared in
+include/vaenar_b200.h, the parameter manifest equals the oracle's (names, shapes, 485 trainable tensors /
+34 725 865 parameters), and compute refuses to run without a CUDA device."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import vaenar_oracle as O
+from oracle.hparams import LJHPS as OLJ, DataBakerHPS as ODB
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    return g.build()
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "vaenar_b200.h")).read()
+    declared = set(re.findall(r"\b(vaenar_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"vaenar_model"}
+    lib = ctypes.CDLL(built)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    from vaenar_tts_b200 import EXPORTS
+    assert set(EXPORTS) == declared, set(EXPORTS) ^ declared
+    assert lib.vaenar_abi_version() == 1
+
+
+@pytest.mark.parametrize("which", ["lj", "db"])
+def test_manifest_matches_oracle(built, which):
+    from vaenar_tts_b200 import VAENAR, LJHPS, DataBakerHPS
+    ohps, hps = (OLJ, LJHPS) if which == "lj" else (ODB, DataBakerHPS)
+    m = VAENAR(hps, device="cpu")
+    P = O.init_params(ohps, seed=0)
+    sd = m.state_dict()
+    assert set(sd) == set(P)
+    for k, v in P.items():
+        assert sd[k].numel() == v.numel(), k
+    tv = m.trainable_variables
+    assert len(tv) == 485
+    assert sum(v.numel() for v in tv) == (34725865 if which == "lj" else 34725865 - 4 * 512)
+    m.load_state_dict(P)
+    back = m.state_dict()
+    for k, v in P.items():
+        assert torch.equal(back[k].reshape(v.shape), v), k
+
+
+def test_default_init_statistics(built):
+    """Keras default initialisers: zero-init projections, orthogonal InvertibleLinear, unit LN/BN scales."""
+    from vaenar_tts_b200 import VAENAR, LJHPS
+    m = VAENAR(LJHPS, device="cpu", seed=1)
+    sd = m.state_dict()
+    assert float(sd["posterior.mu_projection.kernel"].abs().max()) == 0.0
+    assert float(sd["prior.glow.3.affine_coupling.net.shift_proj.kernel"].abs().max()) == 0.0
+    w = sd["prior.glow.0.linear.weight"]
+    assert torch.allclose(w @ w.T, torch.eye(128), atol=1e-5)
+    k = sd["decoder.attentions.0.ffn.dense1.kernel"]
+    lim = (6.0 / (256 + 1024)) ** 0.5
+    assert float(k.abs().max()) <= lim and float(k.abs().max()) > 0.9 * lim
+    assert float(sd["text_encoder.pos_weight"]) == 1.0
+
+
+def test_compute_fails_loudly_without_gpu(built):
+    from vaenar_tts_b200 import VAENAR, LJHPS, VaenarError
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = VAENAR(LJHPS, device="cpu")
+    with pytest.raises(VaenarError):
+        m.inference(torch.zeros(2, 4, dtype=torch.int32), [8, 8], [4, 4])
+    with pytest.raises(VaenarError):
+        m.text_encoder(torch.zeros(2, 4, dtype=torch.int32), [4, 4], pos_step=1.0)
+
+
+def test_workspace_query_and_unsupported_hparams(built):
+    from vaenar_tts_b200 import VAENAR, LJHPS, VaenarError
+    m = VAENAR(LJHPS, device="cpu")
+    a = m._lib.vaenar_workspace_bytes(m._h, 16, 148, 435, 2)
+    b = m._lib.vaenar_workspace_bytes(m._h, 32, 148, 435, 2)
+    assert 0 < a < b < (1 << 31)
+
+    class Bad(LJHPS):
+        class Common(LJHPS.Common):
+            latent_dim = 64
+    with pytest.raises(VaenarError):
+        VAENAR(Bad, device="cpu")

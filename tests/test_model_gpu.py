@@ -1,0 +1,158 @@
+"""Parity of the CUDA path, called through the C ABI behind the reference-shaped VAENAR API, against
+(a) the golden vectors produced by the reference's own sources (tests/golden) and (b) the CPU oracle.
+Tolerances are the north-star ones: mel MAE <= 1e-3, KL / loss relative difference <= 1e-3."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vaenar_oracle as O  # noqa: E402
+from oracle.hparams import LJHPS as OLJ  # noqa: E402
+from golden_util import CASES, load_case, t  # noqa: E402
+
+MEL_MAE_TOL = 1e-3
+REL_TOL = 1e-3
+
+
+def product_hps(ohps):
+    from vaenar_tts_b200 import LJHPS, DataBakerHPS
+    return DataBakerHPS if ohps.name == "databaker" else LJHPS
+
+
+def make_model(ohps, P):
+    from vaenar_tts_b200 import VAENAR
+    m = VAENAR(product_hps(ohps), device="cuda")
+    m.load_state_dict(P)
+    return m
+
+
+def masked_mae(a, b, lengths):
+    a, b = a.float().cpu(), torch.as_tensor(b).float()
+    mask = O.sequence_mask(torch.as_tensor(lengths), a.shape[1], torch.float32)[:, :, None]
+    return float(((a - b).abs() * mask).sum() / (mask.sum() * a.shape[2]))
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double()
+    return float(((a - b).abs() / b.abs().clamp_min(1e-6)).max())
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_golden_submodules(case):
+    """inference.py:125-143 call sequence: text_encoder -> length_predictor -> prior.sample -> decoder"""
+    ohps, g, P = load_case(case)
+    m = make_model(ohps, P)
+    t_len, m_len = t(g, "t_len"), t(g, "m_len")
+    emb = m.text_encoder(t(g, "texts"), t_len, pos_step=ohps.Common.mel_text_len_ratio / 2.0, training=False)
+    ref = t(g, "sub_text_embd")
+    err = float((emb.cpu() - ref).abs().mean())
+    assert err < 2e-3, err
+    pred = m.length_predictor(emb, t_len, training=False)
+    assert rel(pred, g["sub_pred_len"]) < 5e-3
+    z_len = (m_len + 1) // 2
+    z, logp = m.prior.sample(z_len, emb, t_len, training=False, temperature=1.0, epsilon=t(g, "sub_epsilon"))
+    zmask = O.sequence_mask(z_len, z.shape[1], torch.float32)[:, :, None]
+    zerr = float(((z.cpu() - t(g, "sub_z")).abs() * zmask).sum() / (zmask.sum() * z.shape[2]))
+    assert zerr < 2e-3, zerr
+    assert rel(logp, g["sub_logp"]) < REL_TOL
+    # flow round trip (SURVEY.md §4 KAT 1): log_probability(sample(eps)) == logp
+    back = m.prior.log_probability(z, emb, z_lengths=z_len, condition_lengths=t_len)
+    assert rel(back, logp.cpu()) < REL_TOL
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_golden_inference(case):
+    ohps, g, P = load_case(case)
+    m = make_model(ohps, P)
+    mel, ali = m.inference(t(g, "texts"), t(g, "m_len"), t(g, "t_len"), reduction_factor=int(g["rf"]),
+                           epsilon=t(g, "inf_epsilon"))
+    ref = t(g, "inf_mel")
+    assert mel.shape == ref.shape
+    assert masked_mae(mel, ref, t(g, "m_len")) <= MEL_MAE_TOL
+    for k, v in ali.items():
+        assert float((v.cpu() - t(g, "inf_ali_" + k)).abs().max()) < 5e-3
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_golden_call_eval(case):
+    """VAENAR.call forward + ELBO terms (models/models.py:105-197), training=False"""
+    ohps, g, P = load_case(case)
+    m = make_model(ohps, P)
+    rf = int(g["rf"])
+    mel, l2, kl, ll, ali = m(inputs=t(g, "texts"), mel_targets=t(g, "mels"), mel_lengths=t(g, "m_len"),
+                             text_lengths=t(g, "t_len"), reduction_factor=rf, training=False, reduce_loss=False,
+                             eps=t(g, "eval_eps"))
+    assert masked_mae(mel, t(g, "eval_mel"), t(g, "m_len")) <= MEL_MAE_TOL
+    assert rel(l2, g["eval_l2_per"]) < REL_TOL
+    assert rel(kl, g["eval_kl_per"]) < REL_TOL
+    assert rel(ll, g["eval_len_per"]) < 1e-2
+    mel, l2, kl, ll, _ = m(inputs=t(g, "texts"), mel_targets=t(g, "mels"), mel_lengths=t(g, "m_len"),
+                           text_lengths=t(g, "t_len"), reduction_factor=rf, training=False, reduce_loss=True,
+                           eps=t(g, "eval_eps"))
+    assert rel(l2, g["eval_l2"]) < REL_TOL and rel(kl, g["eval_kl"]) < REL_TOL
+    for k, v in ali.items():
+        assert float((v.cpu() - t(g, "eval_ali_" + k)).abs().max()) < 5e-3
+
+
+def test_training_mode_refused():
+    """No silent inference-mode arithmetic when training=True is requested."""
+    ohps, g, P = load_case(list(CASES)[0])
+    m = make_model(ohps, P)
+    with pytest.raises(NotImplementedError):
+        m(inputs=t(g, "texts"), mel_targets=t(g, "mels"), mel_lengths=t(g, "m_len"), text_lengths=t(g, "t_len"),
+          reduction_factor=2, training=True, reduce_loss=True)
+
+
+@pytest.mark.parametrize("B,Tt,Tm", [(16, 148, 870)])
+def test_full_size_vs_oracle(B, Tt, Tm):
+    """BASELINE.json configs[1] (C2) at full size against the CPU oracle, plus size-independent properties:
+    flow round trip and row-stochastic alignments with exact zeros on padded keys."""
+    P = O.init_params(OLJ, seed=5, zero_init_std=0.02)
+    O.randomize_bn_stats(P, seed=6)
+    m = make_model(OLJ, P)
+    texts, mels, t_len, m_len = O.synthetic_batch(OLJ, B, Tt, Tm)
+    Tz = int(((m_len + 1) // 2).max())
+    eps = torch.randn(B, Tz, 128, generator=torch.Generator().manual_seed(1))
+    mel, ali = m.inference(texts, m_len, t_len, reduction_factor=2, epsilon=eps)
+    with torch.no_grad():
+        ref, ref_ali, aux = O.vaenar_inference(P, OLJ, texts, m_len, t_len, 2, eps)
+    mae = masked_mae(mel, ref, m_len)
+    assert mae <= MEL_MAE_TOL, mae
+    a = ali["decoder-attention-1"].cpu()
+    assert float((a.sum(-1) - 1).abs().max()) < 1e-4
+    b = int(torch.argmin(t_len))
+    assert float(a[b, :, : int((m_len[b] + 1) // 2), int(t_len[b]):].abs().max()) == 0.0
+    z_len = (m_len + 1) // 2
+    back = m.prior.log_probability(m._last["z"], m._last["text_embd"], z_lengths=z_len, condition_lengths=t_len)
+    assert rel(back, m._last["logp"].cpu()) < REL_TOL
+    assert rel(m._last["logp"], aux["logp"]) < REL_TOL
+
+
+def test_call_full_size_c1():
+    """BASELINE.json configs[0] (C1: B4, T_text 64, T_mel 256, forward + ELBO) against the oracle."""
+    P = O.init_params(OLJ, seed=9, zero_init_std=0.02)
+    O.randomize_bn_stats(P, seed=10)
+    m = make_model(OLJ, P)
+    texts, mels, t_len, m_len = O.synthetic_batch(OLJ, 4, 64, 256)
+    eps = torch.randn(4, 1, 128, 128, generator=torch.Generator().manual_seed(2))
+    mel, l2, kl, ll, _ = m(inputs=texts, mel_targets=mels, mel_lengths=m_len, text_lengths=t_len, reduction_factor=2,
+                           training=False, reduce_loss=True, eps=eps)
+    with torch.no_grad():
+        rm, rl2, rkl, rll, _, _ = O.vaenar_call(P, OLJ, texts, mels, m_len, t_len, 2, eps)
+    assert masked_mae(mel, rm, m_len) <= MEL_MAE_TOL
+    assert rel(l2, rl2) < REL_TOL and rel(kl, rkl) < REL_TOL and rel(ll, rll) < 1e-2
+
+
+def test_session_graph_matches_eager():
+    """The CUDA-graph serving session returns the same mel as the eager call on the same noise."""
+    from vaenar_tts_b200 import InferenceSession
+    P = O.init_params(OLJ, seed=11, zero_init_std=0.02)
+    m = make_model(OLJ, P)
+    B, Tt, Tm = 4, 40, 200
+    texts, mels, t_len, m_len = O.synthetic_batch(OLJ, B, Tt, Tm)
+    sess = InferenceSession(m, B, Tt, (Tm + 1) // 2, rf=2).capture()
+    sess.set_inputs(texts, t_len, m_len)
+    h_mel = sess.run_e2e(new_noise=True)
+    torch.cuda.synchronize()
+    mel, _ = m.inference(texts, m_len, t_len, reduction_factor=2, epsilon=sess.eps.clone())
+    assert float((h_mel - mel.cpu()).abs().max()) == 0.0

@@ -1,0 +1,306 @@
+// Multi-head scaled-dot-product attention for sm_100a (tcgen05 + TMEM + TMA), one CTA per
+// (query tile of 128, head, batch).  Restates MultiHeadScaledProductAttention.call
+// (modules/attention.py:217-246) with head_dim = 64:
+//
+//   logits = Q K^T / sqrt(64) ; mask = key_len AND query_len (AND lower-triangular if causal)
+//   where(mask, logits, -2^32+1) ; softmax over keys ; ctx = P V ; alignments = P (optional output)
+//
+// A fully masked query row (q >= query_len) yields the UNIFORM distribution 1/Tk over all Tk padded
+// keys, exactly as the reference's constant fill does (attention.py:240-242); masked keys of a live row
+// get exactly 0.  The mask is an in-register predicate from the length arrays -- no mask tensor.
+//
+// Two passes over the key blocks (128 keys each), both on tensor cores:
+//   pass 1: S = Q K^T -> TMEM, softmax warps reduce the row maximum (and the denominator when the
+//           alignments are requested);
+//   pass 2: S again, p = exp(s - max) written as fp16 into 128B-swizzled shared memory (the UMMA
+//           A-operand layout), O += P V accumulated in TMEM; ctx = O / l.
+// No online rescaling of O is ever needed, the whole row never has to be resident, and Tk is unbounded.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 softmax (thread == row).
+#pragma once
+#include "ptx.cuh"
+
+namespace vb {
+
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_BQ = 128;     // queries per CTA
+constexpr int ATT_BK = 128;     // keys per block
+constexpr int ATT_D = 64;       // head dim
+constexpr int ATT_QBYTES = ATT_BQ * ATT_D * 2;       // 16 KB
+constexpr int ATT_KBYTES = ATT_BK * ATT_D * 2;       // 16 KB
+constexpr int ATT_VBYTES = ATT_D * ATT_BK * 2;       // 16 KB (two 64-key panels of 8 KB)
+constexpr int ATT_PBYTES = ATT_BQ * ATT_BK * 2;      // 32 KB (two 64-key panels of 16 KB)
+constexpr int ATT_SMEM = ATT_QBYTES + 2 * ATT_KBYTES + 2 * ATT_VBYTES + 2 * ATT_PBYTES + 1024 + 256;
+
+struct AttnParams {
+  int B, H, Tq, Tk;
+  int q_col0;            // column of head 0 inside the Q tensor map
+  int k_col0;            // column of head 0 inside the K tensor map
+  long vt_row0;          // first V^T row of (batch 0, head 0) for this block
+  const int* q_len;      // [B]
+  const int* k_len;      // [B]
+  int causal;
+  float scale;           // 1 / sqrt(head_dim) / temperature
+  __half* ctx;           // [B*Tq, ctx_ld] fp16, head h at columns h*64
+  int ctx_ld;
+  float* ali;            // optional [B, H, Tq, Tk] fp32
+};
+
+template <bool kWriteAli>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATT_QBYTES;
+  uint8_t* sV = sK + 2 * ATT_KBYTES;
+  uint8_t* sP = sV + 2 * ATT_VBYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_PBYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2]
+  uint64_t* s_empty = bars + 11;  // [2]
+  uint64_t* p_full = bars + 13;   // [2]
+  uint64_t* p_empty = bars + 15;  // [2]
+  uint64_t* o_full = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BQ;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nblk = (p.Tk + ATT_BK - 1) / ATT_BK;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmVt);
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;          // two buffers: columns [0,128) and [128,256)
+  const uint32_t tmem_O = tmem_base + 256;    // columns [256, 320)
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, ATT_QBYTES);
+      tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + h * ATT_D, q0, b);
+      const long vrow = p.vt_row0 + (static_cast<long>(b) * p.H + h) * ATT_D;
+      for (int i = 0; i < 2 * nblk; ++i) {
+        const int j = i % nblk;
+        const int st = i & 1;
+        mbar_wait(&k_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], ATT_KBYTES);
+        tma_load_3d(sK + st * ATT_KBYTES, &tmK, &k_full[st], p.k_col0 + h * ATT_D, j * ATT_BK, b);
+        if (i >= nblk) {
+          const int iv = i - nblk;
+          const int sv = iv & 1;
+          mbar_wait(&v_empty[sv], ((iv >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[sv], ATT_VBYTES);
+          tma_load_2d(sV + sv * ATT_VBYTES, &tmVt, &v_full[sv], j * ATT_BK, static_cast<int>(vrow));
+          tma_load_2d(sV + sv * ATT_VBYTES + ATT_VBYTES / 2, &tmVt, &v_full[sv], j * ATT_BK + 64,
+                      static_cast<int>(vrow));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(ATT_BQ, ATT_BK);   // S: 128 x 128, K = 64
+      constexpr uint32_t idesc_o = umma_idesc_f16(ATT_BQ, ATT_D);    // O: 128 x 64,  K = 128
+      auto issue_pv = [&](int iv) {
+        const int sv = iv & 1;
+        const uint32_t par = (iv >> 1) & 1;
+        mbar_wait(&p_full[sv], par);
+        mbar_wait(&v_full[sv], par);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < ATT_BK / 16; ++k) {
+          const uint64_t adesc =
+              umma_desc_sw128(smem_u32(sP + sv * ATT_PBYTES + (k >> 2) * (ATT_PBYTES / 2))) + 2 * (k & 3);
+          const uint64_t bdesc =
+              umma_desc_sw128(smem_u32(sV + sv * ATT_VBYTES + (k >> 2) * (ATT_VBYTES / 2))) + 2 * (k & 3);
+          umma_f16(tmem_O, adesc, bdesc, idesc_o, (iv > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&p_empty[sv]);
+        umma_commit(&v_empty[sv]);
+      };
+      mbar_wait(q_full, 0);
+      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
+      for (int i = 0; i < 2 * nblk; ++i) {
+        const int st = i & 1;
+        const uint32_t par = (i >> 1) & 1;
+        mbar_wait(&k_full[st], par);
+        mbar_wait(&s_empty[st], par ^ 1);
+        tc_fence_after();
+        const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + st * ATT_KBYTES));
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_f16(tmem_S + st * ATT_BK, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[st]);
+        if (i > nblk) issue_pv(i - nblk - 1);
+      }
+      issue_pv(nblk - 1);
+      umma_commit(o_full);
+    }
+  } else {
+    // ===================== softmax / epilogue warps =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int q = q0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const int qlen = __ldg(p.q_len + b);
+    const int klen = __ldg(p.k_len + b);
+    const bool row_dead = (q >= qlen) || (klen <= 0);      // fully masked row -> uniform over Tk
+    const bool row_store = q < p.Tq;
+    const float sl2 = p.scale * 1.4426950408889634f;       // scale * log2(e)
+    const float inv_tk = 1.0f / static_cast<float>(p.Tk);
+    uint32_t v[32];
+
+    // ---- pass 1: row maximum (and denominator if the alignments are written)
+    float m = -INFINITY;
+    float l = 0.f;
+    for (int i = 0; i < nblk; ++i) {
+      const int st = i & 1;
+      mbar_wait(&s_full[st], (i >> 1) & 1);
+      tc_fence_after();
+      float bm = -INFINITY;
+      for (int c = 0; c < ATT_BK / 32; ++c) {
+        __syncwarp();
+        tmem_ld32(tmem_S + st * ATT_BK + lane_off + c * 32, v);
+        tmem_wait_ld();
+        const int kk0 = i * ATT_BK + c * 32;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int kk = kk0 + e;
+          const bool ok = (kk < klen) && (!p.causal || kk <= q);
+          const float s = ok ? __uint_as_float(v[e]) : -INFINITY;
+          bm = fmaxf(bm, s);
+          if (kWriteAli) v[e] = __float_as_uint(s);
+        }
+        if (kWriteAli && !row_dead) {
+          const float mn = fmaxf(m, bm);
+          if (mn > -INFINITY) {
+            float add = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) add += exp2f((__uint_as_float(v[e]) - mn) * sl2);
+            l = l * exp2f((m - mn) * sl2) + add;
+            m = mn;
+          }
+        }
+      }
+      if (!kWriteAli) m = fmaxf(m, bm);
+      tc_fence_before();
+      mbar_arrive(&s_empty[st]);
+    }
+    if (row_dead) { m = 0.f; l = 1.f; }
+
+    // ---- pass 2: probabilities -> shared memory (A operand of P V), denominators, alignments
+    float lsum = 0.f;
+    const float inv_l = kWriteAli ? 1.0f / l : 1.0f;
+    for (int iv = 0; iv < nblk; ++iv) {
+      const int i = nblk + iv;
+      const int st = i & 1;
+      const int sp = iv & 1;
+      mbar_wait(&s_full[st], (i >> 1) & 1);
+      mbar_wait(&p_empty[sp], ((iv >> 1) & 1) ^ 1);
+      tc_fence_after();
+      uint8_t* prow = sP + sp * ATT_PBYTES + r * 128;
+      for (int c = 0; c < ATT_BK / 32; ++c) {
+        __syncwarp();
+        tmem_ld32(tmem_S + st * ATT_BK + lane_off + c * 32, v);
+        tmem_wait_ld();
+        const int kk0 = iv * ATT_BK + c * 32;
+        float pr[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int kk = kk0 + e;
+          float pe;
+          if (row_dead) {
+            pe = (kk < p.Tk) ? inv_tk : 0.f;
+          } else {
+            const bool ok = (kk < klen) && (!p.causal || kk <= q);
+            pe = ok ? exp2f((__uint_as_float(v[e]) - m) * sl2) : 0.f;
+          }
+          lsum += pe;
+          pr[e] = pe * inv_l;           // normalised already when kWriteAli (inv_l == 1 otherwise)
+        }
+        // 4 x 16-byte chunks into the 128B-swizzled K-major layout: panel = 64 keys, chunk ^= (row & 7)
+        uint8_t* panel = prow + (c >> 1) * (ATT_PBYTES / 2);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int chunk = (c & 1) * 4 + g;
+          uint4 u;
+          u.x = pack_half2(pr[g * 8 + 0], pr[g * 8 + 1]);
+          u.y = pack_half2(pr[g * 8 + 2], pr[g * 8 + 3]);
+          u.z = pack_half2(pr[g * 8 + 4], pr[g * 8 + 5]);
+          u.w = pack_half2(pr[g * 8 + 6], pr[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(panel + ((chunk ^ (r & 7)) << 4)) = u;
+        }
+        if (kWriteAli && row_store) {
+          float* arow = p.ali + ((static_cast<long>(b) * p.H + h) * p.Tq + q) * p.Tk + kk0;
+          for (int e = 0; e < 32 && kk0 + e < p.Tk; ++e) arow[e] = pr[e];
+        }
+      }
+      fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      tc_fence_before();
+      mbar_arrive(&p_full[sp]);
+      mbar_arrive(&s_empty[st]);
+    }
+
+    // ---- epilogue: ctx = O / l
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float on = kWriteAli ? 1.0f : 1.0f / lsum;
+    for (int c = 0; c < ATT_D / 32; ++c) {
+      __syncwarp();
+      tmem_ld32(tmem_O + lane_off + c * 32, v);
+      tmem_wait_ld();
+      if (row_store) {
+        __half* dst = p.ctx + (static_cast<long>(b) * p.Tq + q) * p.ctx_ld + h * ATT_D + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 u;
+          u.x = pack_half2(__uint_as_float(v[j]) * on, __uint_as_float(v[j + 1]) * on);
+          u.y = pack_half2(__uint_as_float(v[j + 2]) * on, __uint_as_float(v[j + 3]) * on);
+          u.z = pack_half2(__uint_as_float(v[j + 4]) * on, __uint_as_float(v[j + 5]) * on);
+          u.w = pack_half2(__uint_as_float(v[j + 6]) * on, __uint_as_float(v[j + 7]) * on);
+          *reinterpret_cast<uint4*>(dst + j) = u;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace vb

@@ -1,0 +1,1503 @@
+// libvaenar_sm100.so -- host-side engine + C ABI (include/vaenar_b200.h) of the B200-native VAENAR-TTS
+// mel-synthesis path.  Owns no device memory: parameters, packed weights and workspace are caller buffers.
+// Every forward below is a fixed sequence of sm_100a kernel launches on the caller's stream (CUDA-graph
+// capturable: no host synchronisation, no allocation).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vaenar_b200.h"
+#include "attention_tc.cuh"
+#include "gemm_tc.cuh"
+#include "simt_kernels.cuh"
+
+using namespace vb;
+
+// ============================================================================ errors
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return -1;
+}
+struct EngineError {
+  std::string msg;
+};
+#define VB_THROW(...)                         \
+  do {                                        \
+    char _b[1024];                            \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);    \
+    throw EngineError{_b};                    \
+  } while (0)
+#define VB_CUDA(x)                                                                              \
+  do {                                                                                          \
+    cudaError_t _e = (x);                                                                       \
+    if (_e != cudaSuccess) VB_THROW("%s failed: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// ============================================================================ TMA descriptor encode
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+      VB_THROW("cuTensorMapEncodeTiled unavailable (no CUDA driver / device?): %s", cudaGetErrorString(e));
+    fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  return fn;
+}
+// fp16 tensor [d2][d1][d0] with d0 contiguous; strides in ELEMENTS; box {b0, b1, 1}; 128B swizzle; OOB -> 0
+static CUtensorMap make_tmap(const void* ptr, int rank, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1,
+                             uint64_t s2, uint32_t b0, uint32_t b1) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1 * 2, s2 * 2};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15) || (rank == 3 && (strides[1] & 15)))
+    VB_THROW("tensor map alignment: ptr %p strides %llu %llu", ptr, (unsigned long long)strides[0],
+             (unsigned long long)strides[1]);
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) VB_THROW("cuTensorMapEncodeTiled failed (%d) dims %llu %llu %llu", (int)r,
+                                  (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2);
+  return m;
+}
+
+// ============================================================================ model description
+struct ParamInfo {
+  std::string name;
+  int ndim;
+  int64_t dims[3];
+  int64_t offset, numel;
+  bool trainable;
+};
+struct PackedMat {
+  int64_t off;   // bytes into the packed arena
+  int N, K;      // [N, K] fp16, K-major
+};
+struct PackPlanOp {
+  int param;         // source parameter index
+  int64_t src_off;   // float offset inside the parameter
+  int K, N, lds;
+  std::string dst;
+  int n_off, k_off, mode;
+};
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+struct vaenar_model {
+  vaenar_hparams_t hp;
+  std::vector<ParamInfo> params;
+  std::map<std::string, int> pidx;
+  int64_t param_floats = 0;
+  std::map<std::string, PackedMat> pmats;
+  std::map<std::string, int64_t> pvecs;   // fp32 vectors in the packed arena (byte offsets)
+  std::vector<PackPlanOp> plan;
+  int64_t packed_bytes = 0;
+  int64_t off_packops = 0, off_ptrs = 0, off_logdet64 = 0, off_winv = 0;
+  int64_t off_Mf = 0, off_cf = 0, off_Mb = 0, off_cb = 0, off_consts = 0;
+  std::vector<PackOp> host_ops;
+  std::vector<const float*> host_ptrs;
+  bool attrs_set = false;
+
+  int add_param(const std::string& n, std::initializer_list<int64_t> dims, bool trainable = true) {
+    ParamInfo p;
+    p.name = n;
+    p.ndim = static_cast<int>(dims.size());
+    p.numel = 1;
+    int i = 0;
+    for (auto d : dims) { p.dims[i++] = d; p.numel *= d; }
+    for (; i < 3; ++i) p.dims[i] = 1;
+    p.offset = param_floats;
+    p.trainable = trainable;
+    param_floats = align_up(param_floats + p.numel, 64);
+    pidx[n] = static_cast<int>(params.size());
+    params.push_back(p);
+    return static_cast<int>(params.size()) - 1;
+  }
+  int P(const std::string& n) const {
+    auto it = pidx.find(n);
+    if (it == pidx.end()) VB_THROW("unknown parameter %s", n.c_str());
+    return it->second;
+  }
+  void add_mat(const std::string& n, int N, int K) {
+    packed_bytes = align_up(packed_bytes, 1024);
+    pmats[n] = PackedMat{packed_bytes, N, K};
+    packed_bytes += static_cast<int64_t>(N) * K * 2;
+  }
+  void add_vec(const std::string& n, int count) {
+    packed_bytes = align_up(packed_bytes, 256);
+    pvecs[n] = packed_bytes;
+    packed_bytes += static_cast<int64_t>(count) * 4;
+  }
+  void add_op(const std::string& dst, int n_off, int k_off, const std::string& param, int64_t src_off, int K, int N,
+              int lds, int mode) {
+    plan.push_back(PackPlanOp{P(param), src_off, K, N, lds, dst, n_off, k_off, mode});
+  }
+};
+
+// ---------------------------------------------------------------------------- manifest
+static void add_dense(vaenar_model& m, const std::string& n, int din, int dout, bool bias = true) {
+  m.add_param(n + ".kernel", {din, dout});
+  if (bias) m.add_param(n + ".bias", {dout});
+}
+static void add_ln(vaenar_model& m, const std::string& n, int d) {
+  m.add_param(n + ".gamma", {d});
+  m.add_param(n + ".beta", {d});
+}
+static void add_conv_bn(vaenar_model& m, const std::string& n, int k, int cin, int cout) {
+  m.add_param(n + ".conv1d.kernel", {k, cin, cout});
+  m.add_param(n + ".conv1d.bias", {cout});
+  m.add_param(n + ".bn.gamma", {cout});
+  m.add_param(n + ".bn.beta", {cout});
+  m.add_param(n + ".bn.moving_mean", {cout}, false);
+  m.add_param(n + ".bn.moving_variance", {cout}, false);
+}
+static void add_ffn(vaenar_model& m, const std::string& n, int d, int hidden) {
+  add_dense(m, n + ".dense1", d, hidden);
+  add_dense(m, n + ".dense2", hidden, d);
+  add_ln(m, n + ".layer_norm", d);
+}
+static void add_xblk(vaenar_model& m, const std::string& n, int d, int mem, int ffn) {
+  for (const char* q : {"query", "key", "value"}) add_dense(m, n + ".self_attention." + q + "_layer", d, d, false);
+  add_dense(m, n + ".att_proj1", 2 * d, d);
+  add_ln(m, n + ".layer_norm1", d);
+  add_dense(m, n + ".cross_attention.query_layer", d, d, false);
+  add_dense(m, n + ".cross_attention.key_layer", mem, d, false);
+  add_dense(m, n + ".cross_attention.value_layer", mem, d, false);
+  add_dense(m, n + ".att_proj2", 2 * d, d);
+  add_ln(m, n + ".layer_norm2", d);
+  add_ffn(m, n + ".ffn", d, ffn);
+}
+
+static int kpad64(int k) { return cdiv(k, 64) * 64; }
+
+// packed operand plan of one CrossAttentionBLK (modules/attention.py:418-452)
+static void plan_xblk(vaenar_model& m, const std::string& pk, const std::string& n, int d, int ffn) {
+  m.add_mat(pk + ".qkv", 3 * d, d);
+  int i = 0;
+  for (const char* q : {"query", "key", "value"})
+    m.add_op(pk + ".qkv", (i++) * d, 0, n + ".self_attention." + q + "_layer.kernel", 0, d, d, d, 0);
+  m.add_mat(pk + ".proj1", d, 2 * d);
+  m.add_op(pk + ".proj1", 0, 0, n + ".att_proj1.kernel", 0, 2 * d, d, d, 0);
+  m.add_mat(pk + ".cq", d, d);
+  m.add_op(pk + ".cq", 0, 0, n + ".cross_attention.query_layer.kernel", 0, d, d, d, 0);
+  m.add_mat(pk + ".proj2", d, 2 * d);
+  m.add_op(pk + ".proj2", 0, 0, n + ".att_proj2.kernel", 0, 2 * d, d, d, 0);
+  m.add_mat(pk + ".ffn1", ffn, d);
+  m.add_op(pk + ".ffn1", 0, 0, n + ".ffn.dense1.kernel", 0, d, ffn, ffn, 0);
+  m.add_mat(pk + ".ffn2", d, ffn);
+  m.add_op(pk + ".ffn2", 0, 0, n + ".ffn.dense2.kernel", 0, ffn, d, d, 0);
+}
+// memory K/V projections of several blocks in ONE matrix: rows [K_0 .. K_{n-1} | V_0 .. V_{n-1}]
+static void plan_memkv(vaenar_model& m, const std::string& pk, const std::vector<std::string>& blks, int mem, int d) {
+  const int nb = static_cast<int>(blks.size());
+  m.add_mat(pk, 2 * nb * d, mem);
+  for (int i = 0; i < nb; ++i) {
+    m.add_op(pk, i * d, 0, blks[i] + ".cross_attention.key_layer.kernel", 0, mem, d, d, 0);
+    m.add_op(pk, nb * d + i * d, 0, blks[i] + ".cross_attention.value_layer.kernel", 0, mem, d, d, 0);
+  }
+}
+// Conv1D kernel [k, cin, cout] -> [cout, k * parts * cpad]; split: parts (hi, hi, lo) to pair with A (hi, lo, hi)
+static void plan_conv(vaenar_model& m, const std::string& pk, const std::string& n, int k, int cin, int cout,
+                      bool split) {
+  const int cp = kpad64(cin), parts = split ? 3 : 1;
+  m.add_mat(pk, cout, k * parts * cp);
+  for (int j = 0; j < k; ++j)
+    for (int p = 0; p < parts; ++p)
+      m.add_op(pk, 0, (j * parts + p) * cp, n + ".conv1d.kernel", static_cast<int64_t>(j) * cin * cout, cin, cout, cout,
+               (split && p == 2) ? 1 : 0);
+  m.add_vec(pk + ".bn_scale", cout);
+  m.add_vec(pk + ".bn_shift", cout);
+}
+
+static void build_model(vaenar_model& m) {
+  const vaenar_hparams_t& h = m.hp;
+  // ---- supported envelope of the hand-written kernels
+  if (h.enc_att_dim / h.enc_heads != 64 || h.dec_att_dim / h.dec_heads != 64 ||
+      h.posterior_att_dim / h.posterior_heads != 64 || h.prior_att_dim / h.prior_heads != 64)
+    VB_THROW("kernels are specialised for head_dim 64");
+  if (h.latent_dim != FLOW_DIM) VB_THROW("flow kernels are specialised for latent_dim 128");
+  if (h.enc_hidden != 512 || h.embd_dim != 512) VB_THROW("encoder width must be 512 (LayerNorm epilogue tile)");
+  if (h.dec_att_dim != 256 || h.posterior_att_dim != 256 || h.prior_att_dim != 256 || h.enc_att_dim != 256 ||
+      h.posterior_pre_hidden != 256 || h.post_filters != 256)
+    VB_THROW("decoder/posterior/prior width must be 256 (LayerNorm epilogue tile)");
+  if (h.enc_conv_kernel * 1 > kMaxSegs || h.post_kernel * 3 > kMaxSegs) VB_THROW("conv kernel too wide");
+  const int E = h.enc_hidden, O = h.out_dim, L = h.latent_dim;
+
+  // ---- parameters
+  m.add_param("text_encoder.emb_layer.embeddings", {h.vocab_size, h.embd_dim});
+  m.add_param("text_encoder.pos_weight", {1});
+  {
+    int cin = h.embd_dim;
+    for (int i = 0; i < h.enc_n_conv; ++i) {
+      add_conv_bn(m, "text_encoder.prenet.conv_stack." + std::to_string(i), h.enc_conv_kernel, cin, E);
+      cin = E;
+    }
+  }
+  add_dense(m, "text_encoder.prenet.projection", E, E);
+  for (int i = 0; i < h.enc_n_blk; ++i) {
+    const std::string n = "text_encoder.self_attentions." + std::to_string(i);
+    for (const char* q : {"query", "key", "value"}) add_dense(m, n + ".attention." + q + "_layer", E, h.enc_att_dim, false);
+    add_dense(m, n + ".att_proj", E + h.enc_att_dim, E);
+    add_ln(m, n + ".layer_norm", E);
+    add_ffn(m, n + ".ffn", E, h.enc_ffn);
+  }
+  add_dense(m, "length_predictor.projection", E, 1);
+  m.add_param("posterior.pos_weight", {1});
+  add_dense(m, "posterior.prenet.dense1", O, h.posterior_pre_hidden);
+  add_dense(m, "posterior.prenet.dense2", h.posterior_pre_hidden, h.posterior_pre_hidden);
+  for (int i = 0; i < h.posterior_nblk; ++i)
+    add_xblk(m, "posterior.attentions." + std::to_string(i), h.posterior_att_dim, E, h.posterior_ffn);
+  add_dense(m, "posterior.mu_projection", h.posterior_att_dim, L);
+  add_dense(m, "posterior.logvar_projection", h.posterior_att_dim, L);
+  for (int s = 0; s < h.prior_n_blk; ++s) {
+    const std::string g = "prior.glow." + std::to_string(s);
+    m.add_param(g + ".actnorm.log_scale", {L});
+    m.add_param(g + ".actnorm.bias", {L});
+    m.add_param(g + ".linear.weight", {L, L});
+    const std::string n = g + ".affine_coupling.net";
+    m.add_param(n + ".pos_weight", {1});
+    add_dense(m, n + ".pre_projection", L / 2, h.prior_att_dim);
+    for (int j = 0; j < h.prior_n_tblk; ++j)
+      add_xblk(m, n + ".attentions." + std::to_string(j), h.prior_att_dim, E, h.prior_ffn);
+    add_dense(m, n + ".log_scale_proj", h.prior_att_dim, L / 2);
+    add_dense(m, n + ".shift_proj", h.prior_att_dim, L / 2);
+  }
+  add_dense(m, "decoder.pre_projection", L, h.dec_att_dim);
+  for (int i = 0; i < h.dec_nblk; ++i) add_xblk(m, "decoder.attentions." + std::to_string(i), h.dec_att_dim, E, h.dec_ffn);
+  add_dense(m, "decoder.out_projection", h.dec_att_dim, O * h.max_reduction_factor);
+  {
+    int cin = O;
+    for (int i = 0; i < h.post_n_conv; ++i) {
+      add_conv_bn(m, "decoder.postnet.conv_stack." + std::to_string(i), h.post_kernel, cin, h.post_filters);
+      cin = h.post_filters;
+    }
+  }
+  add_dense(m, "decoder.residual_projection", h.post_filters, O);
+
+  // ---- packed operand plan
+  {
+    int cin = h.embd_dim;
+    for (int i = 0; i < h.enc_n_conv; ++i) {
+      plan_conv(m, "enc.conv" + std::to_string(i), "text_encoder.prenet.conv_stack." + std::to_string(i),
+                h.enc_conv_kernel, cin, E, false);
+      cin = E;
+    }
+  }
+  m.add_mat("enc.proj", E, E);
+  m.add_op("enc.proj", 0, 0, "text_encoder.prenet.projection.kernel", 0, E, E, E, 0);
+  for (int i = 0; i < h.enc_n_blk; ++i) {
+    const std::string n = "text_encoder.self_attentions." + std::to_string(i), pk = "enc.blk" + std::to_string(i);
+    const int A = h.enc_att_dim;
+    m.add_mat(pk + ".qkv", 3 * A, E);
+    int c = 0;
+    for (const char* q : {"query", "key", "value"})
+      m.add_op(pk + ".qkv", (c++) * A, 0, n + ".attention." + q + "_layer.kernel", 0, E, A, A, 0);
+    m.add_mat(pk + ".proj", E, E + A);
+    m.add_op(pk + ".proj", 0, 0, n + ".att_proj.kernel", 0, E + A, E, E, 0);
+    m.add_mat(pk + ".ffn1", h.enc_ffn, E);
+    m.add_op(pk + ".ffn1", 0, 0, n + ".ffn.dense1.kernel", 0, E, h.enc_ffn, h.enc_ffn, 0);
+    m.add_mat(pk + ".ffn2", E, h.enc_ffn);
+    m.add_op(pk + ".ffn2", 0, 0, n + ".ffn.dense2.kernel", 0, h.enc_ffn, E, E, 0);
+  }
+  // posterior
+  m.add_mat("post.pre1", h.posterior_pre_hidden, kpad64(O));
+  m.add_op("post.pre1", 0, 0, "posterior.prenet.dense1.kernel", 0, O, h.posterior_pre_hidden, h.posterior_pre_hidden, 0);
+  m.add_mat("post.pre2", h.posterior_pre_hidden, h.posterior_pre_hidden);
+  m.add_op("post.pre2", 0, 0, "posterior.prenet.dense2.kernel", 0, h.posterior_pre_hidden, h.posterior_pre_hidden,
+           h.posterior_pre_hidden, 0);
+  {
+    std::vector<std::string> blks;
+    for (int i = 0; i < h.posterior_nblk; ++i) {
+      const std::string n = "posterior.attentions." + std::to_string(i);
+      plan_xblk(m, "post.blk" + std::to_string(i), n, h.posterior_att_dim, h.posterior_ffn);
+      blks.push_back(n);
+    }
+    plan_memkv(m, "post.kv", blks, E, h.posterior_att_dim);
+  }
+  // models/models.py:136 swaps the names: mu_projection's output is used as the LOG-VARIANCE, logvar_projection's
+  // as the MEAN.  Packed order = [log-variance | mean] as EPI_POSTERIOR expects.
+  m.add_mat("post.out", 2 * L, h.posterior_att_dim);
+  m.add_op("post.out", 0, 0, "posterior.mu_projection.kernel", 0, h.posterior_att_dim, L, L, 0);
+  m.add_op("post.out", L, 0, "posterior.logvar_projection.kernel", 0, h.posterior_att_dim, L, L, 0);
+  m.add_vec("post.out.bias", 2 * L);
+  // prior
+  {
+    std::vector<std::string> blks;
+    for (int s = 0; s < h.prior_n_blk; ++s) {
+      const std::string n = "prior.glow." + std::to_string(s) + ".affine_coupling.net", pk = "prior." + std::to_string(s);
+      m.add_mat(pk + ".pre", h.prior_att_dim, kpad64(L / 2));
+      m.add_op(pk + ".pre", 0, 0, n + ".pre_projection.kernel", 0, L / 2, h.prior_att_dim, h.prior_att_dim, 0);
+      for (int j = 0; j < h.prior_n_tblk; ++j) {
+        plan_xblk(m, pk + ".blk" + std::to_string(j), n + ".attentions." + std::to_string(j), h.prior_att_dim, h.prior_ffn);
+        blks.push_back(n + ".attentions." + std::to_string(j));
+      }
+      m.add_mat(pk + ".out", L, h.prior_att_dim);
+      m.add_op(pk + ".out", 0, 0, n + ".log_scale_proj.kernel", 0, h.prior_att_dim, L / 2, L / 2, 0);
+      m.add_op(pk + ".out", L / 2, 0, n + ".shift_proj.kernel", 0, h.prior_att_dim, L / 2, L / 2, 0);
+      m.add_vec(pk + ".out.bias", L);
+    }
+    plan_memkv(m, "prior.kv", blks, E, h.prior_att_dim);
+  }
+  // decoder
+  m.add_mat("dec.pre", h.dec_att_dim, L);
+  m.add_op("dec.pre", 0, 0, "decoder.pre_projection.kernel", 0, L, h.dec_att_dim, h.dec_att_dim, 0);
+  {
+    std::vector<std::string> blks;
+    for (int i = 0; i < h.dec_nblk; ++i) {
+      const std::string n = "decoder.attentions." + std::to_string(i);
+      plan_xblk(m, "dec.blk" + std::to_string(i), n, h.dec_att_dim, h.dec_ffn);
+      blks.push_back(n);
+    }
+    plan_memkv(m, "dec.kv", blks, E, h.dec_att_dim);
+  }
+  m.add_mat("dec.out", O * h.max_reduction_factor, h.dec_att_dim);
+  m.add_op("dec.out", 0, 0, "decoder.out_projection.kernel", 0, h.dec_att_dim, O * h.max_reduction_factor,
+           O * h.max_reduction_factor, 0);
+  {
+    int cin = O;
+    for (int i = 0; i < h.post_n_conv; ++i) {
+      plan_conv(m, "dec.post" + std::to_string(i), "decoder.postnet.conv_stack." + std::to_string(i), h.post_kernel, cin,
+                h.post_filters, true);
+      cin = h.post_filters;
+    }
+  }
+  m.add_mat("dec.res", O, 3 * h.post_filters);
+  for (int p = 0; p < 3; ++p)
+    m.add_op("dec.res", 0, p * h.post_filters, "decoder.residual_projection.kernel", 0, h.post_filters, O, O, p == 2 ? 1 : 0);
+  // flow constants
+  const int S = h.prior_n_blk;
+  auto region = [&](int64_t bytes) {
+    m.packed_bytes = align_up(m.packed_bytes, 256);
+    const int64_t o = m.packed_bytes;
+    m.packed_bytes += bytes;
+    return o;
+  };
+  m.off_Mf = region(static_cast<int64_t>(S) * L * L * 4);
+  m.off_Mb = region(static_cast<int64_t>(S) * L * L * 4);
+  m.off_winv = region(static_cast<int64_t>(S) * L * L * 4);
+  m.off_cf = region(S * L * 4);
+  m.off_cb = region(S * L * 4);
+  m.off_consts = region(S * 2 * 4);
+  m.off_logdet64 = region(S * 8);
+  m.off_ptrs = region(3 * S * 8);
+  m.off_packops = region(static_cast<int64_t>(m.plan.size()) * sizeof(PackOp));
+  m.packed_bytes = align_up(m.packed_bytes, 1024);
+}
+
+// ============================================================================ execution context
+struct Ctx {
+  vaenar_model* m;
+  const float* params;
+  uint8_t* packed;
+  uint8_t* ws;
+  int64_t ws_bytes;
+  int64_t ws_off = 0, ws_peak = 0;
+  bool dry = false;
+  cudaStream_t stream;
+
+  template <typename T>
+  T* alloc(int64_t count) {
+    ws_off = align_up(ws_off, 1024);
+    const int64_t o = ws_off;
+    ws_off += count * static_cast<int64_t>(sizeof(T));
+    if (ws_off > ws_peak) ws_peak = ws_off;
+    if (!dry && ws_off > ws_bytes) VB_THROW("workspace too small: need %lld bytes, have %lld", (long long)ws_off, (long long)ws_bytes);
+    return dry ? nullptr : reinterpret_cast<T*>(ws + o);
+  }
+  const float* P(const std::string& n) const { return dry ? nullptr : params + m->params[m->P(n)].offset; }
+  const __half* W(const std::string& n) const {
+    auto it = m->pmats.find(n);
+    if (it == m->pmats.end()) VB_THROW("unknown packed matrix %s", n.c_str());
+    return dry ? nullptr : reinterpret_cast<const __half*>(packed + it->second.off);
+  }
+  const PackedMat& WM(const std::string& n) const { return m->pmats.at(n); }
+  float* V(const std::string& n) const {
+    auto it = m->pvecs.find(n);
+    if (it == m->pvecs.end()) VB_THROW("unknown packed vector %s", n.c_str());
+    return dry ? nullptr : reinterpret_cast<float*>(packed + it->second);
+  }
+};
+
+// ---- launch accounting + optional per-launch timing (bench.py roofline; never active inside graph capture)
+struct KernelStat {
+  double flops = 0;     // algorithmic FLOPs of the instrumented launches
+  double bytes = 0;     // algorithmic HBM bytes (operands read once + outputs written once)
+  long launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+};
+static long g_launch_count = 0;
+static bool g_profile = false;
+static std::map<std::string, KernelStat> g_stats;
+static std::string g_profile_json;
+
+static void check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) VB_THROW("launch of %s failed: %s", what, cudaGetErrorString(e));
+  ++g_launch_count;
+}
+struct ProfileScope {
+  KernelStat* st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStream_t stream;
+  ProfileScope(const std::string& cls, double flops, double bytes, cudaStream_t s) : stream(s) {
+    if (!g_profile) return;
+    st = &g_stats[cls];
+    st->flops += flops;
+    st->bytes += bytes;
+    st->launches += 1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, stream);
+  }
+  ~ProfileScope() {
+    if (!st) return;
+    cudaEventRecord(e1, stream);
+    st->events.emplace_back(e0, e1);
+  }
+};
+
+static void set_attrs(vaenar_model* m) {
+  static bool done = false;
+  if (done) return;
+  VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes));
+  VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmemBytes));
+  VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<512>::kSmemBytes));
+  VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+  VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+  VB_CUDA(cudaFuncSetAttribute(slogdet128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOW_DIM * (FLOW_DIM + 1) * 8));
+  VB_CUDA(cudaFuncSetAttribute(inverse128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FLOW_DIM * (2 * FLOW_DIM + 1) + FLOW_DIM) * 4));
+  VB_CUDA(cudaFuncSetAttribute(flow_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FLOW_DIM * FLOW_DIM + 32 * FLOW_DIM) * 4));
+  done = true;
+  (void)m;
+}
+
+// ============================================================================ launch helpers
+struct AOp {
+  const __half* p = nullptr;
+  int ld = 0;   // row stride in elements
+  int K = 0;    // valid inner extent
+};
+
+static void segs_plain(GemmParams& p, int K) {
+  p.nseg = 1;
+  p.seg_map[0] = 0; p.seg_shift[0] = 0; p.seg_kblocks[0] = cdiv(K, 64);
+  p.alg_k = K;
+}
+static void segs_concat(GemmParams& p, int K0, int K1) {
+  p.nseg = 2;
+  p.seg_map[0] = 0; p.seg_shift[0] = 0; p.seg_kblocks[0] = cdiv(K0, 64);
+  p.seg_map[1] = 1; p.seg_shift[1] = 0; p.seg_kblocks[1] = cdiv(K1, 64);
+  p.alg_k = K0 + K1;
+}
+// taps x (hi | lo | hi) when split; row shift j - (taps-1)/2  (Keras 'same' padding, stride 1)
+static void segs_conv(GemmParams& p, int taps, int cin, bool split) {
+  const int parts = split ? 3 : 1;
+  p.nseg = taps * parts;
+  p.alg_k = taps * cin;
+  for (int j = 0; j < taps; ++j)
+    for (int q = 0; q < parts; ++q) {
+      const int s = j * parts + q;
+      p.seg_map[s] = (split && q == 1) ? 1 : 0;
+      p.seg_shift[s] = j - (taps - 1) / 2;
+      p.seg_kblocks[s] = cdiv(cin, 64);
+    }
+}
+
+// A operands: [batches, rows, K]; W: packed [Nrows, Ktot]; output tile selection by block_n.
+static void run_gemm(Ctx& c, int block_n, AOp a0, AOp a1, int batches, int rows, const __half* W, int Ktot, int Nrows,
+                     GemmParams p) {
+  if (c.dry) return;
+  int tk = 0;
+  for (int s = 0; s < p.nseg; ++s) tk += p.seg_kblocks[s];
+  if (tk * 64 != Ktot) VB_THROW("gemm: segments cover %d of K %d", tk * 64, Ktot);
+  if ((p.mode == EPI_LN || p.mode == EPI_COUPLING || p.mode == EPI_POSTERIOR) && p.N != block_n)
+    VB_THROW("gemm: row-wise epilogue needs BLOCK_N == N (%d vs %d)", block_n, p.N);
+  p.batches = batches;
+  p.rows = rows;
+  p.tiles_per_batch = cdiv(rows, GEMM_BLOCK_M);
+  if (p.seq_T <= 0) { p.seq_T = rows; p.seq_B = batches; }
+  if (!a1.p) a1 = a0;
+  const CUtensorMap tA0 = make_tmap(a0.p, 3, a0.K, rows, batches, a0.ld, static_cast<uint64_t>(rows) * a0.ld, 64, 128);
+  const CUtensorMap tA1 = make_tmap(a1.p, 3, a1.K, rows, batches, a1.ld, static_cast<uint64_t>(rows) * a1.ld, 64, 128);
+  const CUtensorMap tB = make_tmap(W, 2, Ktot, Nrows, 1, Ktot, 0, 64, block_n > 256 ? 256 : block_n);
+  dim3 grid(batches * p.tiles_per_batch, cdiv(p.N, block_n));
+  const double Mrows = static_cast<double>(batches) * rows;
+  const double kalg = p.alg_k > 0 ? p.alg_k : Ktot;   // algorithmic K: no padding, no split-fp16 triple
+  const char* cls = p.mode == EPI_LN ? "gemm_ln" : (p.nseg >= 5 ? "gemm_conv" : (p.mode == EPI_QKV ? "gemm_qkv" : "gemm_plain"));
+  ProfileScope prof(cls, 2.0 * Mrows * p.N * kalg, Mrows * kalg * 2 + static_cast<double>(p.N) * Ktot * 2 + Mrows * p.N * 6, c.stream);
+  switch (block_n) {
+    case 128: gemm_tc_kernel<128><<<grid, GEMM_THREADS, GemmCfg<128>::kSmemBytes, c.stream>>>(tA0, tA1, tB, p); break;
+    case 256: gemm_tc_kernel<256><<<grid, GEMM_THREADS, GemmCfg<256>::kSmemBytes, c.stream>>>(tA0, tA1, tB, p); break;
+    case 512: gemm_tc_kernel<512><<<grid, GEMM_THREADS, GemmCfg<512>::kSmemBytes, c.stream>>>(tA0, tA1, tB, p); break;
+    default: VB_THROW("unsupported BLOCK_N %d", block_n);
+  }
+  check_launch("gemm_tc_kernel");
+}
+
+static GemmParams gp() {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.ln_eps = 1e-3f;   // Keras LayerNormalization default epsilon
+  return p;
+}
+
+struct AttnCall {
+  const __half* q; int q_ld; int q_col0; int Tq;
+  const __half* k; int k_ld; int k_col0; int Tk;
+  const __half* vt; long vt_rows; int vt_ld; long vt_row0;
+  const int* q_len; const int* k_len;
+  int causal;
+  __half* ctx; int ctx_ld;
+  float* ali;
+};
+static void run_attention(Ctx& c, int B, int H, const AttnCall& a) {
+  if (c.dry) return;
+  AttnParams p;
+  p.B = B; p.H = H; p.Tq = a.Tq; p.Tk = a.Tk;
+  p.q_col0 = a.q_col0; p.k_col0 = a.k_col0; p.vt_row0 = a.vt_row0;
+  p.q_len = a.q_len; p.k_len = a.k_len; p.causal = a.causal;
+  p.scale = 1.0f / sqrtf(static_cast<float>(ATT_D));   // attention.py:227-229, temperature 1.0
+  p.ctx = a.ctx; p.ctx_ld = a.ctx_ld; p.ali = a.ali;
+  const CUtensorMap tQ = make_tmap(a.q, 3, a.q_ld, a.Tq, B, a.q_ld, static_cast<uint64_t>(a.Tq) * a.q_ld, 64, 128);
+  const CUtensorMap tK = make_tmap(a.k, 3, a.k_ld, a.Tk, B, a.k_ld, static_cast<uint64_t>(a.Tk) * a.k_ld, 64, 128);
+  const CUtensorMap tV = make_tmap(a.vt, 2, a.Tk, a.vt_rows, 1, a.vt_ld, 0, 64, 64);
+  dim3 grid(cdiv(a.Tq, ATT_BQ), H, B);
+  const double work = static_cast<double>(B) * H * a.Tq * a.Tk;
+  ProfileScope prof(a.causal ? "attn_self" : (a.ali ? "attn_cross_ali" : "attn_cross"), 4.0 * work * ATT_D,
+                    static_cast<double>(B) * H * ATT_D * 2 * (2.0 * a.Tq + 2.0 * a.Tk) + (a.ali ? work * 4 : 0), c.stream);
+  if (a.ali) attention_tc_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, c.stream>>>(tQ, tK, tV, p);
+  else attention_tc_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, c.stream>>>(tQ, tK, tV, p);
+  check_launch("attention_tc_kernel");
+}
+
+static void run_cast(Ctx& c, const float* in, __half* out, int64_t n) {
+  if (c.dry) return;
+  const int64_t thr = (n + 3) / 4;
+  cast_f32_to_f16_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, c.stream>>>(in, out, n);
+  check_launch("cast");
+}
+static void run_pe(Ctx& c, float* out, int T, int D, float step) {
+  if (c.dry) return;
+  pe_table_kernel<<<T, 256, 0, c.stream>>>(out, T, D, step);
+  check_launch("pe_table");
+}
+static int vt_pad(int T) { return cdiv(T, 64) * 64; }
+
+// ============================================================================ blocks
+struct Stream2 {   // fp32 residual stream + its fp16 operand copy, [rows, d]
+  float* f;
+  __half* h;
+};
+struct MemKV {     // projected memory of all blocks of a module
+  __half* k;       // [B*Tt, nblk*d]
+  __half* vt;      // [nblk*B*H*64, tpad]
+  int nblk, d, tpad;
+};
+
+// K/V projections of the text memory for all blocks of a module, one GEMM (attention.py:219-220 hoisted)
+static MemKV memory_kv(Ctx& c, const std::string& wname, const __half* emb_h, int B, int Tt, int E, int nblk, int d, int H) {
+  MemKV kv;
+  kv.nblk = nblk; kv.d = d; kv.tpad = vt_pad(Tt);
+  kv.k = c.alloc<__half>(static_cast<int64_t>(B) * Tt * nblk * d);
+  kv.vt = c.alloc<__half>(static_cast<int64_t>(nblk) * B * H * 64 * kv.tpad);
+  GemmParams p = gp();
+  p.mode = EPI_QKV; p.N = 2 * nblk * d;
+  segs_plain(p, E);
+  p.seq_T = Tt; p.seq_B = B;
+  p.n_rowmajor = nblk * d; p.out_h = kv.k; p.ld_h = nblk * d;
+  p.vt = kv.vt; p.vt_ld = kv.tpad; p.heads = H;
+  run_gemm(c, 256, AOp{emb_h, E, E}, AOp{}, 1, B * Tt, c.W(wname), E, 2 * nblk * d, p);
+  return kv;
+}
+
+struct XblkBufs {
+  __half* qk;    // [rows, 2d]  self Q | K
+  __half* vt;    // [B*H*64, tpad]
+  __half* ctx;   // [rows, d]
+  __half* q;     // [rows, d]
+  __half* hid;   // [rows, ffn]
+  Stream2 s, cst;
+  int tpad;
+};
+static XblkBufs xblk_bufs(Ctx& c, int B, int T, int d, int H, int ffn) {
+  XblkBufs b;
+  const int64_t rows = static_cast<int64_t>(B) * T;
+  b.tpad = vt_pad(T);
+  b.qk = c.alloc<__half>(rows * 2 * d);
+  b.vt = c.alloc<__half>(static_cast<int64_t>(B) * H * 64 * b.tpad);
+  b.ctx = c.alloc<__half>(rows * d);
+  b.q = c.alloc<__half>(rows * d);
+  b.hid = c.alloc<__half>(rows * ffn);
+  b.s.f = c.alloc<float>(rows * d); b.s.h = c.alloc<__half>(rows * d);
+  b.cst.f = c.alloc<float>(rows * d); b.cst.h = c.alloc<__half>(rows * d);
+  return b;
+}
+
+// CrossAttentionBLK.call (modules/attention.py:436-452); x updated in place.
+static void xblk_fwd(Ctx& c, const std::string& pk, const std::string& pn, Stream2 x, const XblkBufs& b, int B, int T,
+                     int d, int H, int ffn, const int* q_len, const MemKV& kv, int kv_blk, int Tt, const int* t_len,
+                     float* ali) {
+  const int rows = B * T;
+  {  // self-attention projections: Q | K row-major, V transposed
+    GemmParams p = gp();
+    p.mode = EPI_QKV; p.N = 3 * d; segs_plain(p, d);
+    p.seq_T = T; p.seq_B = B; p.n_rowmajor = 2 * d; p.out_h = b.qk; p.ld_h = 2 * d;
+    p.vt = b.vt; p.vt_ld = b.tpad; p.heads = H;
+    run_gemm(c, 256, AOp{x.h, d, d}, AOp{}, 1, rows, c.W(pk + ".qkv"), d, 3 * d, p);
+  }
+  run_attention(c, B, H, AttnCall{b.qk, 2 * d, 0, T, b.qk, 2 * d, d, T, b.vt, static_cast<long>(B) * H * 64, b.tpad, 0,
+                                  q_len, q_len, 1, b.ctx, d, nullptr});
+  {  // LN1(att_proj1([x ; a1]) + x)
+    GemmParams p = gp();
+    p.mode = EPI_LN; p.N = d; segs_concat(p, d, d);
+    p.bias = c.P(pn + ".att_proj1.bias"); p.residual = x.f; p.res_ld = d;
+    p.ln_gamma = c.P(pn + ".layer_norm1.gamma"); p.ln_beta = c.P(pn + ".layer_norm1.beta");
+    p.out_f32 = b.s.f; p.ld_f32 = d; p.out_h = b.s.h; p.ld_h = d;
+    run_gemm(c, d, AOp{x.h, d, d}, AOp{b.ctx, d, d}, 1, rows, c.W(pk + ".proj1"), 2 * d, d, p);
+  }
+  {  // cross-attention query projection
+    GemmParams p = gp();
+    p.mode = EPI_PLAIN; p.N = d; segs_plain(p, d);
+    p.out_h = b.q; p.ld_h = d;
+    run_gemm(c, 128, AOp{b.s.h, d, d}, AOp{}, 1, rows, c.W(pk + ".cq"), d, d, p);
+  }
+  run_attention(c, B, H, AttnCall{b.q, d, 0, T, kv.k, kv.nblk * kv.d, kv_blk * kv.d, Tt, kv.vt,
+                                  static_cast<long>(kv.nblk) * B * H * 64, kv.tpad, static_cast<long>(kv_blk) * B * H * 64,
+                                  q_len, t_len, 0, b.ctx, d, ali});
+  {  // LN2(att_proj2([s ; a2]) + s)
+    GemmParams p = gp();
+    p.mode = EPI_LN; p.N = d; segs_concat(p, d, d);
+    p.bias = c.P(pn + ".att_proj2.bias"); p.residual = b.s.f; p.res_ld = d;
+    p.ln_gamma = c.P(pn + ".layer_norm2.gamma"); p.ln_beta = c.P(pn + ".layer_norm2.beta");
+    p.out_f32 = b.cst.f; p.ld_f32 = d; p.out_h = b.cst.h; p.ld_h = d;
+    run_gemm(c, d, AOp{b.s.h, d, d}, AOp{b.ctx, d, d}, 1, rows, c.W(pk + ".proj2"), 2 * d, d, p);
+  }
+  {  // FFN (modules/utils.py:48-53)
+    GemmParams p = gp();
+    p.mode = EPI_PLAIN; p.N = ffn; segs_plain(p, d); p.act = 1;
+    p.bias = c.P(pn + ".ffn.dense1.bias"); p.out_h = b.hid; p.ld_h = ffn;
+    run_gemm(c, 128, AOp{b.cst.h, d, d}, AOp{}, 1, rows, c.W(pk + ".ffn1"), d, ffn, p);
+  }
+  {
+    GemmParams p = gp();
+    p.mode = EPI_LN; p.N = d; segs_plain(p, ffn);
+    p.bias = c.P(pn + ".ffn.dense2.bias"); p.residual = b.cst.f; p.res_ld = d;
+    p.ln_gamma = c.P(pn + ".ffn.layer_norm.gamma"); p.ln_beta = c.P(pn + ".ffn.layer_norm.beta");
+    p.out_f32 = x.f; p.ld_f32 = d; p.out_h = x.h; p.ld_h = d;
+    run_gemm(c, d, AOp{b.hid, ffn, ffn}, AOp{}, 1, rows, c.W(pk + ".ffn2"), ffn, d, p);
+  }
+}
+
+// ============================================================================ modules
+// TransformerEncoder.call (modules/encoder.py:79-93), inference mode. Writes text_embd fp32 [B,Tt,E].
+static void encoder_fwd(Ctx& c, const int* texts, const int* t_len, int B, int Tt, float pos_step, float* text_embd) {
+  const vaenar_hparams_t& h = c.m->hp;
+  const int E = h.enc_hidden, A = h.enc_att_dim, H = h.enc_heads, F = h.enc_ffn;
+  const int64_t rows = static_cast<int64_t>(B) * Tt;
+  const int64_t mark = c.ws_off;
+  __half* xa = c.alloc<__half>(rows * E);
+  __half* xb = c.alloc<__half>(rows * E);
+  float* hf = c.alloc<float>(rows * E);
+  __half* hh = c.alloc<__half>(rows * E);
+  __half* qk = c.alloc<__half>(rows * 2 * A);
+  const int tpad = vt_pad(Tt);
+  __half* vt = c.alloc<__half>(static_cast<int64_t>(B) * H * 64 * tpad);
+  __half* ctx = c.alloc<__half>(rows * A);
+  __half* hid = c.alloc<__half>(rows * F);
+  float* pe = c.alloc<float>(static_cast<int64_t>(Tt) * E);
+  if (!c.dry) {
+    embed_kernel<<<static_cast<unsigned>(rows), 128, 0, c.stream>>>(texts, c.P("text_encoder.emb_layer.embeddings"), xa,
+                                                                   static_cast<int>(rows), E, h.vocab_size);
+    check_launch("embed");
+  }
+  run_pe(c, pe, Tt, E, pos_step);
+  int cin = h.embd_dim;
+  for (int i = 0; i < h.enc_n_conv; ++i) {   // ConvPreNet (modules/utils.py:21-38): conv -> relu -> BN
+    const std::string pk = "enc.conv" + std::to_string(i), pn = "text_encoder.prenet.conv_stack." + std::to_string(i);
+    GemmParams p = gp();
+    p.mode = EPI_PLAIN; p.N = E; p.act = 1; segs_conv(p, h.enc_conv_kernel, cin, false);
+    p.bias = c.P(pn + ".conv1d.bias"); p.ch_scale = c.V(pk + ".bn_scale"); p.ch_shift = c.V(pk + ".bn_shift");
+    p.out_h = xb; p.ld_h = E;
+    run_gemm(c, 128, AOp{xa, cin, cin}, AOp{}, B, Tt, c.W(pk), c.WM(pk).K, E, p);
+    std::swap(xa, xb);
+    cin = E;
+  }
+  {  // prenet projection + pos_weight * PE (encoder.py:84-86)
+    GemmParams p = gp();
+    p.mode = EPI_PLAIN; p.N = E; segs_plain(p, E);
+    p.bias = c.P("text_encoder.prenet.projection.bias");
+    p.seq_T = Tt; p.seq_B = B;
+    p.add_table = pe; p.add_ld = E; p.add_scale = c.P("text_encoder.pos_weight");
+    p.out_f32 = text_embd; p.ld_f32 = E; p.out_h = xb; p.ld_h = E;
+    run_gemm(c, 128, AOp{xa, E, E}, AOp{}, 1, static_cast<int>(rows), c.W("enc.proj"), E, E, p);
+    std::swap(xa, xb);
+  }
+  for (int i = 0; i < h.enc_n_blk; ++i) {   // SelfAttentionBLK (modules/attention.py:405-415)
+    const std::string pk = "enc.blk" + std::to_string(i), pn = "text_encoder.self_attentions." + std::to_string(i);
+    {
+      GemmParams p = gp();
+      p.mode = EPI_QKV; p.N = 3 * A; segs_plain(p, E);
+      p.seq_T = Tt; p.seq_B = B; p.n_rowmajor = 2 * A; p.out_h = qk; p.ld_h = 2 * A;
+      p.vt = vt; p.vt_ld = tpad; p.heads = H;
+      run_gemm(c, 256, AOp{xa, E, E}, AOp{}, 1, static_cast<int>(rows), c.W(pk + ".qkv"), E, 3 * A, p);
+    }
+    run_attention(c, B, H, AttnCall{qk, 2 * A, 0, Tt, qk, 2 * A, A, Tt, vt, static_cast<long>(B) * H * 64, tpad, 0, t_len,
+                                    t_len, 0, ctx, A, nullptr});
+    {
+      GemmParams p = gp();
+      p.mode = EPI_LN; p.N = E; segs_concat(p, E, A);
+      p.bias = c.P(pn + ".att_proj.bias"); p.residual = text_embd; p.res_ld = E;
+      p.ln_gamma = c.P(pn + ".layer_norm.gamma"); p.ln_beta = c.P(pn + ".layer_norm.beta");
+      p.out_f32 = hf; p.ld_f32 = E; p.out_h = hh; p.ld_h = E;
+      run_gemm(c, E, AOp{xa, E, E}, AOp{ctx, A, A}, 1, static_cast<int>(rows), c.W(pk + ".proj"), E + A, E, p);
+    }
+    {
+      GemmParams p = gp();
+      p.mode = EPI_PLAIN; p.N = F; p.act = 1; segs_plain(p, E);
+      p.bias = c.P(pn + ".ffn.dense1.bias"); p.out_h = hid; p.ld_h = F;
+      run_gemm(c, 128, AOp{hh, E, E}, AOp{}, 1, static_cast<int>(rows), c.W(pk + ".ffn1"), E, F, p);
+    }
+    {
+      GemmParams p = gp();
+      p.mode = EPI_LN; p.N = E; segs_plain(p, F);
+      p.bias = c.P(pn + ".ffn.dense2.bias"); p.residual = hf; p.res_ld = E;
+      p.ln_gamma = c.P(pn + ".ffn.layer_norm.gamma"); p.ln_beta = c.P(pn + ".ffn.layer_norm.beta");
+      p.out_f32 = text_embd; p.ld_f32 = E; p.out_h = xa; p.ld_h = E;
+      run_gemm(c, E, AOp{hid, F, F}, AOp{}, 1, static_cast<int>(rows), c.W(pk + ".ffn2"), F, E, p);
+    }
+  }
+  c.ws_off = mark;
+}
+
+static void length_predictor_fwd(Ctx& c, const float* text_embd, const int* t_len, int B, int Tt, float* out) {
+  if (c.dry) return;
+  length_predictor_kernel<<<B, 256, 0, c.stream>>>(text_embd, c.P("length_predictor.projection.kernel"),
+                                                  c.P("length_predictor.projection.bias"), t_len, out, Tt,
+                                                  c.m->hp.enc_hidden);
+  check_launch("length_predictor");
+}
+
+// One flow step's conditioner + coupling (modules/flow.py:223-257, modules/transform.py:45-59)
+static void coupling_step(Ctx& c, int s, bool backward, float* z, __half* zh, float* row_acc, Stream2 x, const XblkBufs& xb,
+                          const float* pe, const MemKV& kv, int B, int Tz, int Tt, const int* z_len, const int* t_len) {
+  const vaenar_hparams_t& h = c.m->hp;
+  const int d = h.prior_att_dim, H = h.prior_heads, F = h.prior_ffn, L = h.latent_dim;
+  const int rows = B * Tz;
+  const bool upper = (s % 2 == 0);           // modules/prior.py:85-87
+  const int cond_off = upper ? 0 : L / 2;    // conditioning half
+  const int zp_off = upper ? L / 2 : 0;      // transformed half
+  const std::string pk = "prior." + std::to_string(s), pn = "prior.glow." + std::to_string(s) + ".affine_coupling.net";
+  {
+    GemmParams p = gp();
+    p.mode = EPI_PLAIN; p.N = d; segs_plain(p, L / 2);
+    p.bias = c.P(pn + ".pre_projection.bias");
+    p.seq_T = Tz; p.seq_B = B; p.add_table = pe; p.add_ld = d; p.add_scale = c.P(pn + ".pos_weight");
+    p.out_f32 = x.f; p.ld_f32 = d; p.out_h = x.h; p.ld_h = d;
+    run_gemm(c, 128, AOp{c.dry ? nullptr : zh + cond_off, L, L / 2}, AOp{}, 1, rows, c.W(pk + ".pre"), kpad64(L / 2), d, p);
+  }
+  for (int j = 0; j < h.prior_n_tblk; ++j)
+    xblk_fwd(c, pk + ".blk" + std::to_string(j), pn + ".attentions." + std::to_string(j), x, xb, B, Tz, d, H, F, z_len, kv,
+             s * h.prior_n_tblk + j, Tt, t_len, nullptr);
+  {
+    GemmParams p = gp();
+    p.mode = EPI_COUPLING; p.N = L; segs_plain(p, d);
+    p.seq_T = Tz; p.seq_B = B;
+    p.bias = c.V(pk + ".out.bias");
+    p.z = z; p.z_h = zh; p.z_ld = L; p.zp_off = zp_off; p.backward = backward ? 1 : 0;
+    p.row_acc = row_acc; p.lengths = z_len;
+    run_gemm(c, 128, AOp{x.h, d, d}, AOp{}, 1, rows, c.W(pk + ".out"), d, L, p);
+  }
+  (void)cond_off;
+}
+
+static void flow_linear(Ctx& c, float* z, __half* zh, const float* M, const float* cvec, int64_t rows) {
+  if (c.dry) return;
+  flow_linear_kernel<<<static_cast<unsigned>((rows + 31) / 32), 256, (FLOW_DIM * FLOW_DIM + 32 * FLOW_DIM) * 4, c.stream>>>(
+      z, zh, M, cvec, rows);
+  check_launch("flow_linear");
+}
+
+struct PriorBufs {
+  __half* emb_h;
+  __half* zh;
+  float* row_acc;
+  float* base;
+  float* pe;
+  Stream2 x;
+  XblkBufs xb;
+  MemKV kv;
+};
+static PriorBufs prior_setup(Ctx& c, const float* text_embd, int B, int Tt, int Tz) {
+  const vaenar_hparams_t& h = c.m->hp;
+  const int d = h.prior_att_dim, E = h.enc_hidden, L = h.latent_dim;
+  const int64_t rows = static_cast<int64_t>(B) * Tz;
+  PriorBufs b;
+  b.emb_h = c.alloc<__half>(static_cast<int64_t>(B) * Tt * E);
+  run_cast(c, text_embd, b.emb_h, static_cast<int64_t>(B) * Tt * E);
+  b.zh = c.alloc<__half>(rows * L);
+  b.row_acc = c.alloc<float>(rows);
+  b.base = c.alloc<float>(B);
+  b.pe = c.alloc<float>(static_cast<int64_t>(Tz) * d);
+  b.x.f = c.alloc<float>(rows * d);
+  b.x.h = c.alloc<__half>(rows * d);
+  b.xb = xblk_bufs(c, B, Tz, d, h.prior_heads, h.prior_ffn);
+  b.kv = memory_kv(c, "prior.kv", b.emb_h, B, Tt, E, h.prior_n_blk * h.prior_n_tblk, d, h.prior_heads);
+  run_pe(c, b.pe, Tz, d, 1.0f);
+  if (!c.dry) VB_CUDA(cudaMemsetAsync(b.row_acc, 0, rows * sizeof(float), c.stream));
+  return b;
+}
+
+// TransformerPrior.sample (modules/prior.py:154-169); z holds epsilon on entry.
+static void prior_sample(Ctx& c, const float* text_embd, const int* t_len, const int* z_len, int B, int Tt, int Tz,
+                         float* z, float* logp) {
+  const vaenar_hparams_t& h = c.m->hp;
+  const int L = h.latent_dim;
+  const int64_t mark = c.ws_off;
+  PriorBufs b = prior_setup(c, text_embd, B, Tt, Tz);
+  if (!c.dry) {
+    base_logprob_kernel<<<B, 256, 0, c.stream>>>(z, z_len, b.base, Tz, L);
+    check_launch("base_logprob");
+  }
+  const float* Mf = c.dry ? nullptr : reinterpret_cast<const float*>(c.packed + c.m->off_Mf);
+  const float* cf = c.dry ? nullptr : reinterpret_cast<const float*>(c.packed + c.m->off_cf);
+  for (int s = 0; s < h.prior_n_blk; ++s) {
+    flow_linear(c, z, b.zh, c.dry ? nullptr : Mf + static_cast<int64_t>(s) * L * L, c.dry ? nullptr : cf + s * L,
+                static_cast<int64_t>(B) * Tz);
+    coupling_step(c, s, false, z, b.zh, b.row_acc, b.x, b.xb, b.pe, b.kv, B, Tz, Tt, z_len, t_len);
+  }
+  if (!c.dry) {
+    prior_logp_finalize_kernel<<<B, 256, 0, c.stream>>>(b.base, b.row_acc,
+                                                       reinterpret_cast<const float*>(c.packed + c.m->off_consts),
+                                                       h.prior_n_blk, z_len, logp, Tz, -1.0f);
+    check_launch("prior_logp_finalize");
+  }
+  c.ws_off = mark;
+}
+
+// TransformerPrior.log_probability (modules/prior.py:119-152)
+static void prior_logprob(Ctx& c, const float* z_in, const float* text_embd, const int* t_len, const int* z_len, int B,
+                          int Tt, int Tz, float* logp) {
+  const vaenar_hparams_t& h = c.m->hp;
+  const int L = h.latent_dim;
+  const int64_t rows = static_cast<int64_t>(B) * Tz;
+  const int64_t mark = c.ws_off;
+  float* z = c.alloc<float>(rows * L);
+  PriorBufs b = prior_setup(c, text_embd, B, Tt, Tz);
+  if (!c.dry) VB_CUDA(cudaMemcpyAsync(z, z_in, rows * L * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  run_cast(c, z, b.zh, rows * L);
+  const float* Mb = c.dry ? nullptr : reinterpret_cast<const float*>(c.packed + c.m->off_Mb);
+  const float* cb = c.dry ? nullptr : reinterpret_cast<const float*>(c.packed + c.m->off_cb);
+  for (int s = h.prior_n_blk - 1; s >= 0; --s) {
+    coupling_step(c, s, true, z, b.zh, b.row_acc, b.x, b.xb, b.pe, b.kv, B, Tz, Tt, z_len, t_len);
+    flow_linear(c, z, b.zh, c.dry ? nullptr : Mb + static_cast<int64_t>(s) * L * L, c.dry ? nullptr : cb + s * L, rows);
+  }
+  if (!c.dry) {
+    base_logprob_kernel<<<B, 256, 0, c.stream>>>(z, z_len, b.base, Tz, L);
+    check_launch("base_logprob");
+    // backward log-dets: coupling -sum log scale (already signed in row_acc), linear -len*log|det W|, actnorm -len*sum s
+    prior_logp_finalize_kernel<<<B, 256, 0, c.stream>>>(b.base, b.row_acc,
+                                                       reinterpret_cast<const float*>(c.packed + c.m->off_consts),
+                                                       h.prior_n_blk, z_len, logp, Tz, 1.0f);
+    check_launch("prior_logp_finalize");
+  }
+  c.ws_off = mark;
+}
+
+// TransformerPosterior.call + reparameterize + log_probability (modules/posterior.py:20-72,115-130)
+static void posterior_fwd(Ctx& c, const float* mels, const float* text_embd, const int* t_len, const int* z_len,
+                          const float* eps, int B, int Tt, int Tm, int Tz, int rf, float* z, float* logq) {
+  const vaenar_hparams_t& h = c.m->hp;
+  const int d = h.posterior_att_dim, H = h.posterior_heads, F = h.posterior_ffn, E = h.enc_hidden, L = h.latent_dim,
+            O = h.out_dim;
+  const int64_t rows = static_cast<int64_t>(B) * Tz;
+  const int64_t mark = c.ws_off;
+  __half* emb_h = c.alloc<__half>(static_cast<int64_t>(B) * Tt * E);
+  run_cast(c, text_embd, emb_h, static_cast<int64_t>(B) * Tt * E);
+  __half* rm = c.alloc<__half>(rows * O);
+  __half* a1 = c.alloc<__half>(rows * d);
+  Stream2 x{c.alloc<float>(rows * d), c.alloc<__half>(rows * d)};
+  __half* zh = c.alloc<__half>(rows * L);
+  float* row_acc = c.alloc<float>(rows);
+  float* pe = c.alloc<float>(static_cast<int64_t>(Tz) * d);
+  XblkBufs xb = xblk_bufs(c, B, Tz, d, H, F);
+  MemKV kv = memory_kv(c, "post.kv", emb_h, B, Tt, E, h.posterior_nblk, d, H);
+  run_pe(c, pe, Tz, d, 1.0f);
+  if (!c.dry) {
+    reduce_mels_kernel<<<static_cast<unsigned>(rows), 96, 0, c.stream>>>(mels, rm, B, Tm, Tz, rf, O);
+    check_launch("reduce_mels");
+    VB_CUDA(cudaMemsetAsync(row_acc, 0, rows * sizeof(float), c.stream));
+  }
+  {  // PreNet dense1 + relu (modules/utils.py:13-18); dropout inactive (training=False)
+    GemmParams p = gp();
+    p.mode = EPI_PLAIN; p.N = d; p.act = 1; segs_plain(p, O);
+    p.bias = c.P("posterior.prenet.dense1.bias"); p.out_h = a1; p.ld_h = d;
+    run_gemm(c, 128, AOp{rm, O, O}, AOp{}, 1, static_cast<int>(rows), c.W("post.pre1"), kpad64(O), d, p);
+  }
+  {  // dense2 + relu, then + pos_weight * PE (posterior.py:118-121)
+    GemmParams p = gp();
+    p.mode = EPI_PLAIN; p.N = d; p.act = 1; segs_plain(p, d);
+    p.bias = c.P("posterior.prenet.dense2.bias");
+    p.seq_T = Tz; p.seq_B = B; p.add_table = pe; p.add_ld = d; p.add_scale = c.P("posterior.pos_weight");
+    p.out_f32 = x.f; p.ld_f32 = d; p.out_h = x.h; p.ld_h = d;
+    run_gemm(c, 128, AOp{a1, d, d}, AOp{}, 1, static_cast<int>(rows), c.W("post.pre2"), d, d, p);
+  }
+  for (int i = 0; i < h.posterior_nblk; ++i)
+    xblk_fwd(c, "post.blk" + std::to_string(i), "posterior.attentions." + std::to_string(i), x, xb, B, Tz, d, H, F, z_len, kv,
+             i, Tt, t_len, nullptr);
+  {
+    GemmParams p = gp();
+    p.mode = EPI_POSTERIOR; p.N = 2 * L; segs_plain(p, d);
+    p.seq_T = Tz; p.seq_B = B;
+    p.bias = c.V("post.out.bias"); p.eps_in = eps; p.z = z; p.z_h = zh; p.z_ld = L; p.row_acc = row_acc; p.lengths = z_len;
+    run_gemm(c, 2 * L, AOp{x.h, d, d}, AOp{}, 1, static_cast<int>(rows), c.W("post.out"), d, 2 * L, p);
+  }
+  if (!c.dry) {
+    row_sum_kernel<<<B, 256, 0, c.stream>>>(row_acc, logq, Tz);
+    check_launch("row_sum");
+  }
+  c.ws_off = mark;
+}
+
+// TransformerDecoder.call (modules/decoder.py:181-199), inference mode
+static void decoder_fwd(Ctx& c, const float* z, const float* text_embd, const int* z_len, const int* t_len, int B, int Tt,
+                        int Tz, int rf, float* initial, float* mel, float* ali) {
+  const vaenar_hparams_t& h = c.m->hp;
+  const int d = h.dec_att_dim, H = h.dec_heads, F = h.dec_ffn, E = h.enc_hidden, L = h.latent_dim, O = h.out_dim,
+            C = h.post_filters;
+  if (rf < 1 || rf > h.max_reduction_factor) VB_THROW("reduction factor %d outside [1, %d]", rf, h.max_reduction_factor);
+  const int64_t rows = static_cast<int64_t>(B) * Tz;
+  const int Tm = Tz * rf;
+  const int64_t mrows = static_cast<int64_t>(B) * Tm;
+  const int64_t mark = c.ws_off;
+  __half* emb_h = c.alloc<__half>(static_cast<int64_t>(B) * Tt * E);
+  run_cast(c, text_embd, emb_h, static_cast<int64_t>(B) * Tt * E);
+  __half* zh = c.alloc<__half>(rows * L);
+  run_cast(c, z, zh, rows * L);
+  Stream2 x{c.alloc<float>(rows * d), c.alloc<__half>(rows * d)};
+  XblkBufs xb = xblk_bufs(c, B, Tz, d, H, F);
+  MemKV kv = memory_kv(c, "dec.kv", emb_h, B, Tt, E, h.dec_nblk, d, H);
+  __half* ini_h = c.alloc<__half>(mrows * O);
+  __half* ini_l = c.alloc<__half>(mrows * O);
+  __half* pa_h = c.alloc<__half>(mrows * C);
+  __half* pa_l = c.alloc<__half>(mrows * C);
+  __half* pb_h = c.alloc<__half>(mrows * C);
+  __half* pb_l = c.alloc<__half>(mrows * C);
+  {  // pre_projection (no positional encoding in the decoder, decoder.py:186-188)
+    GemmParams p = gp();
+    p.mode = EPI_PLAIN; p.N = d; segs_plain(p, L);
+    p.bias = c.P("decoder.pre_projection.bias");
+    p.out_f32 = x.f; p.ld_f32 = d; p.out_h = x.h; p.ld_h = d;
+    run_gemm(c, 128, AOp{zh, L, L}, AOp{}, 1, static_cast<int>(rows), c.W("dec.pre"), L, d, p);
+  }
+  for (int i = 0; i < h.dec_nblk; ++i)
+    xblk_fwd(c, "dec.blk" + std::to_string(i), "decoder.attentions." + std::to_string(i), x, xb, B, Tz, d, H, F, z_len, kv, i,
+             Tt, t_len, ali ? ali + static_cast<int64_t>(i) * B * H * Tz * Tt : nullptr);
+  {  // out_projection, first rf*80 columns only (decoder.py:193); [B*Tz, rf*80] == [B*Tz*rf, 80]
+    GemmParams p = gp();
+    p.mode = EPI_PLAIN; p.N = rf * O; segs_plain(p, d);
+    p.bias = c.P("decoder.out_projection.bias");
+    p.out_f32 = initial; p.ld_f32 = rf * O; p.out_h = ini_h; p.out_lo = ini_l; p.ld_h = rf * O;
+    run_gemm(c, 128, AOp{x.h, d, d}, AOp{}, 1, static_cast<int>(rows), c.W("dec.out"), d, rf * O, p);
+  }
+  // PostNet (modules/utils.py:98-115): conv -> tanh (last: identity) -> BN; split-fp16 operands
+  __half *in_h = ini_h, *in_l = ini_l, *out_h = pa_h, *out_l = pa_l;
+  int cin = O;
+  for (int i = 0; i < h.post_n_conv; ++i) {
+    const std::string pk = "dec.post" + std::to_string(i), pn = "decoder.postnet.conv_stack." + std::to_string(i);
+    GemmParams p = gp();
+    p.mode = EPI_PLAIN; p.N = C; p.act = (i < h.post_n_conv - 1) ? 2 : 0; segs_conv(p, h.post_kernel, cin, true);
+    p.bias = c.P(pn + ".conv1d.bias"); p.ch_scale = c.V(pk + ".bn_scale"); p.ch_shift = c.V(pk + ".bn_shift");
+    p.out_h = out_h; p.out_lo = out_l; p.ld_h = C;
+    run_gemm(c, 128, AOp{in_h, cin, cin}, AOp{in_l, cin, cin}, B, Tm, c.W(pk), c.WM(pk).K, C, p);
+    in_h = out_h; in_l = out_l;
+    out_h = (in_h == pa_h) ? pb_h : pa_h;
+    out_l = (in_l == pa_l) ? pb_l : pa_l;
+    cin = C;
+  }
+  {  // residual_projection + initial (decoder.py:197-198)
+    GemmParams p = gp();
+    p.mode = EPI_PLAIN; p.N = O;
+    p.nseg = 3;
+    for (int q = 0; q < 3; ++q) { p.seg_map[q] = (q == 1) ? 1 : 0; p.seg_shift[q] = 0; p.seg_kblocks[q] = cdiv(C, 64); }
+    p.alg_k = C;
+    p.bias = c.P("decoder.residual_projection.bias"); p.residual = initial; p.res_ld = O;
+    p.out_f32 = mel; p.ld_f32 = O;
+    run_gemm(c, 128, AOp{in_h, C, C}, AOp{in_l, C, C}, 1, static_cast<int>(mrows), c.W("dec.res"), 3 * C, O, p);
+  }
+  c.ws_off = mark;
+}
+
+// ---- small loss kernels (models/models.py:88-103)
+__global__ void length_loss_kernel(const float* pred, const int* lens, float* out, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    const float d = logf(pred[b]) - logf(static_cast<float>(lens[b]));
+    out[b] = d * d;
+  }
+}
+__global__ void kl_kernel(const float* logq, const float* logp, float* out, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) out[b] = logq[b] - logp[b];
+}
+
+// VAENAR.call forward (models/models.py:105-197), training=False, n_sample = 1
+static void elbo_fwd(Ctx& c, const int* texts, const float* mels, const int* m_len, const int* t_len, const int* z_len,
+                     const float* eps, int B, int Tt, int Tm, int Tz, int rf, float* mel_out, float* l2, float* kl,
+                     float* len_loss, float* ali) {
+  const vaenar_hparams_t& h = c.m->hp;
+  const int E = h.enc_hidden, L = h.latent_dim, O = h.out_dim;
+  const int64_t mark = c.ws_off;
+  float* emb = c.alloc<float>(static_cast<int64_t>(B) * Tt * E);
+  float* z = c.alloc<float>(static_cast<int64_t>(B) * Tz * L);
+  float* ini = c.alloc<float>(static_cast<int64_t>(B) * Tz * rf * O);
+  float* fin = c.alloc<float>(static_cast<int64_t>(B) * Tz * rf * O);
+  float* pred = c.alloc<float>(B);
+  float* logq = c.alloc<float>(B);
+  float* logp = c.alloc<float>(B);
+  encoder_fwd(c, texts, t_len, B, Tt, h.mel_text_len_ratio / static_cast<float>(rf), emb);
+  length_predictor_fwd(c, emb, t_len, B, Tt, pred);
+  posterior_fwd(c, mels, emb, t_len, z_len, eps, B, Tt, Tm, Tz, rf, z, logq);
+  decoder_fwd(c, z, emb, z_len, t_len, B, Tt, Tz, rf, ini, fin, ali);
+  prior_logprob(c, z, emb, t_len, z_len, B, Tt, Tz, logp);
+  if (!c.dry) {
+    length_loss_kernel<<<cdiv(B, 128), 128, 0, c.stream>>>(pred, m_len, len_loss, B);
+    l2_loss_kernel<<<B, 256, 0, c.stream>>>(fin, Tz * rf, mels, Tm, m_len, l2, O, 0);
+    l2_loss_kernel<<<B, 256, 0, c.stream>>>(ini, Tz * rf, mels, Tm, m_len, l2, O, 1);
+    kl_kernel<<<cdiv(B, 128), 128, 0, c.stream>>>(logq, logp, kl, B);
+    check_launch("loss kernels");
+    VB_CUDA(cudaMemcpy2DAsync(mel_out, static_cast<size_t>(Tm) * O * 4, fin, static_cast<size_t>(Tz) * rf * O * 4,
+                              static_cast<size_t>(Tm) * O * 4, B, cudaMemcpyDeviceToDevice, c.stream));
+  }
+  c.ws_off = mark;
+}
+
+static void inference_fwd(Ctx& c, const int* texts, const int* t_len, const int* z_len, int B, int Tt, int Tz, int rf,
+                          float* z_io, float* text_embd, float* mel, float* ali, float* logp) {
+  const vaenar_hparams_t& h = c.m->hp;
+  const int64_t mark = c.ws_off;
+  float* ini = c.alloc<float>(static_cast<int64_t>(B) * Tz * rf * h.out_dim);
+  encoder_fwd(c, texts, t_len, B, Tt, h.mel_text_len_ratio / static_cast<float>(rf), text_embd);
+  prior_sample(c, text_embd, t_len, z_len, B, Tt, Tz, z_io, logp);
+  decoder_fwd(c, z_io, text_embd, z_len, t_len, B, Tt, Tz, rf, ini, mel, ali);
+  c.ws_off = mark;
+}
+
+// ============================================================================ weight packing
+static void pack_weights(vaenar_model* m, const float* params, uint8_t* packed, cudaStream_t stream) {
+  const vaenar_hparams_t& h = m->hp;
+  VB_CUDA(cudaMemsetAsync(packed, 0, m->packed_bytes, stream));
+  // 1. transposed fp16 operand matrices
+  m->host_ops.clear();
+  int maxK = 0, maxN = 0;
+  for (const PackPlanOp& o : m->plan) {
+    const PackedMat& pm = m->pmats.at(o.dst);
+    PackOp op;
+    op.src = params + m->params[o.param].offset + o.src_off;
+    op.dst = reinterpret_cast<__half*>(packed + pm.off) + static_cast<int64_t>(o.n_off) * pm.K + o.k_off;
+    op.K = o.K; op.N = o.N; op.lds = o.lds; op.ldd = pm.K; op.mode = o.mode;
+    if (o.n_off + o.N > pm.N || o.k_off + o.K > pm.K) VB_THROW("pack op outside %s", o.dst.c_str());
+    m->host_ops.push_back(op);
+    maxK = std::max(maxK, o.K);
+    maxN = std::max(maxN, o.N);
+  }
+  PackOp* dops = reinterpret_cast<PackOp*>(packed + m->off_packops);
+  VB_CUDA(cudaMemcpyAsync(dops, m->host_ops.data(), m->host_ops.size() * sizeof(PackOp), cudaMemcpyHostToDevice, stream));
+  const int nops = static_cast<int>(m->host_ops.size());
+  for (int o0 = 0; o0 < nops; o0 += 65535) {
+    dim3 grid(cdiv(maxN, 32), cdiv(maxK, 32), std::min(65535, nops - o0));
+    pack_weights_kernel<<<grid, dim3(32, 8), 0, stream>>>(dops + o0);
+    check_launch("pack_weights");
+  }
+  auto PP = [&](const std::string& n) { return params + m->params[m->P(n)].offset; };
+  auto VV = [&](const std::string& n) { return reinterpret_cast<float*>(packed + m->pvecs.at(n)); };
+  // 2. inference BatchNorm -> affine
+  auto fold = [&](const std::string& pk, const std::string& pn, int C) {
+    bn_fold_kernel<<<cdiv(C, 128), 128, 0, stream>>>(PP(pn + ".bn.gamma"), PP(pn + ".bn.beta"), PP(pn + ".bn.moving_mean"),
+                                                    PP(pn + ".bn.moving_variance"), 1e-3f, VV(pk + ".bn_scale"),
+                                                    VV(pk + ".bn_shift"), C);
+  };
+  for (int i = 0; i < h.enc_n_conv; ++i)
+    fold("enc.conv" + std::to_string(i), "text_encoder.prenet.conv_stack." + std::to_string(i), h.enc_hidden);
+  for (int i = 0; i < h.post_n_conv; ++i)
+    fold("dec.post" + std::to_string(i), "decoder.postnet.conv_stack." + std::to_string(i), h.post_filters);
+  // 3. concatenated biases
+  const int L = h.latent_dim;
+  concat2_kernel<<<cdiv(2 * L, 128), 128, 0, stream>>>(PP("posterior.mu_projection.bias"), L,
+                                                      PP("posterior.logvar_projection.bias"), L, VV("post.out.bias"));
+  for (int s = 0; s < h.prior_n_blk; ++s) {
+    const std::string n = "prior.glow." + std::to_string(s) + ".affine_coupling.net";
+    concat2_kernel<<<1, 128, 0, stream>>>(PP(n + ".log_scale_proj.bias"), L / 2, PP(n + ".shift_proj.bias"), L / 2,
+                                          VV("prior." + std::to_string(s) + ".out.bias"));
+  }
+  check_launch("bn_fold/concat");
+  // 4. flow: float64 log|det W|, fp32 inverse, ActNorm folded maps
+  const int S = h.prior_n_blk;
+  m->host_ptrs.assign(3 * S, nullptr);
+  for (int s = 0; s < S; ++s) {
+    const std::string g = "prior.glow." + std::to_string(s);
+    m->host_ptrs[s] = PP(g + ".linear.weight");
+    m->host_ptrs[S + s] = PP(g + ".actnorm.log_scale");
+    m->host_ptrs[2 * S + s] = PP(g + ".actnorm.bias");
+  }
+  const float** dptrs = reinterpret_cast<const float**>(packed + m->off_ptrs);
+  VB_CUDA(cudaMemcpyAsync(dptrs, m->host_ptrs.data(), 3 * S * sizeof(float*), cudaMemcpyHostToDevice, stream));
+  double* ld64 = reinterpret_cast<double*>(packed + m->off_logdet64);
+  float* winv = reinterpret_cast<float*>(packed + m->off_winv);
+  slogdet128_kernel<<<S, FLOW_DIM, FLOW_DIM * (FLOW_DIM + 1) * 8, stream>>>(dptrs, ld64);
+  inverse128_kernel<<<S, 2 * FLOW_DIM, (FLOW_DIM * (2 * FLOW_DIM + 1) + FLOW_DIM) * 4, stream>>>(dptrs, winv);
+  flow_fold_kernel<<<S, FLOW_DIM, 0, stream>>>(dptrs, dptrs + S, dptrs + 2 * S, winv, ld64,
+                                              reinterpret_cast<float*>(packed + m->off_Mf),
+                                              reinterpret_cast<float*>(packed + m->off_cf),
+                                              reinterpret_cast<float*>(packed + m->off_Mb),
+                                              reinterpret_cast<float*>(packed + m->off_cb),
+                                              reinterpret_cast<float*>(packed + m->off_consts));
+  check_launch("flow prepare");
+}
+
+// ============================================================================ C ABI
+#define API_BEGIN try {
+#define API_END                          \
+  }                                      \
+  catch (const EngineError& e) {         \
+    g_err = e.msg;                       \
+    return -1;                           \
+  }                                      \
+  catch (const std::exception& e) {      \
+    g_err = e.what();                    \
+    return -2;                           \
+  }                                      \
+  return 0;
+
+static Ctx make_ctx(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes, void* stream) {
+  if (!h) VB_THROW("null handle");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) VB_THROW("no CUDA device: the B200 path has no CPU fallback");
+  set_attrs(h);
+  Ctx c;
+  c.m = h; c.params = params; c.packed = const_cast<uint8_t*>(static_cast<const uint8_t*>(packed));
+  c.ws = static_cast<uint8_t*>(ws); c.ws_bytes = ws_bytes; c.stream = static_cast<cudaStream_t>(stream);
+  return c;
+}
+
+extern "C" {
+
+const char* vaenar_last_error(void) { return g_err.c_str(); }
+int vaenar_abi_version(void) { return 1; }
+
+int vaenar_create(const vaenar_hparams_t* hps, vaenar_handle_t* out) {
+  API_BEGIN
+  if (!hps || !out) VB_THROW("null argument");
+  vaenar_model* m = new vaenar_model();
+  m->hp = *hps;
+  try {
+    build_model(*m);
+  } catch (...) {
+    delete m;
+    throw;
+  }
+  *out = m;
+  API_END
+}
+int vaenar_destroy(vaenar_handle_t h) {
+  delete h;
+  return 0;
+}
+int vaenar_num_params(vaenar_handle_t h) { return h ? static_cast<int>(h->params.size()) : -1; }
+const char* vaenar_param_name(vaenar_handle_t h, int i) { return h->params[i].name.c_str(); }
+int vaenar_param_ndim(vaenar_handle_t h, int i) { return h->params[i].ndim; }
+int64_t vaenar_param_dim(vaenar_handle_t h, int i, int d) { return h->params[i].dims[d]; }
+int64_t vaenar_param_offset(vaenar_handle_t h, int i) { return h->params[i].offset; }
+int vaenar_param_trainable(vaenar_handle_t h, int i) { return h->params[i].trainable ? 1 : 0; }
+int64_t vaenar_param_floats(vaenar_handle_t h) { return h->param_floats; }
+int64_t vaenar_packed_bytes(vaenar_handle_t h) { return h->packed_bytes; }
+
+int64_t vaenar_workspace_bytes(vaenar_handle_t h, int B, int T_text, int T_z, int rf) {
+  try {
+    Ctx c;
+    c.m = h; c.params = nullptr; c.packed = nullptr; c.ws = nullptr; c.ws_bytes = 0; c.dry = true; c.stream = nullptr;
+    inference_fwd(c, nullptr, nullptr, nullptr, B, T_text, T_z, rf, nullptr, nullptr, nullptr, nullptr, nullptr);
+    elbo_fwd(c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, B, T_text, T_z * rf, T_z, rf, nullptr, nullptr, nullptr,
+             nullptr, nullptr);
+    return align_up(c.ws_peak, 1024) + 4096;
+  } catch (const EngineError& e) {
+    g_err = e.msg;
+    return -1;
+  }
+}
+
+int vaenar_pack_weights(vaenar_handle_t h, const float* params, void* packed, void* stream) {
+  API_BEGIN
+  Ctx c = make_ctx(h, params, packed, nullptr, 0, stream);
+  pack_weights(h, params, static_cast<uint8_t*>(packed), c.stream);
+  API_END
+}
+
+int vaenar_text_encoder_fwd(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
+                            const int32_t* texts, const int32_t* text_lengths, int B, int T_text, float pos_step,
+                            float* text_embd, void* stream) {
+  API_BEGIN
+  Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
+  encoder_fwd(c, texts, text_lengths, B, T_text, pos_step, text_embd);
+  API_END
+}
+
+int vaenar_length_predictor_fwd(vaenar_handle_t h, const float* params, const float* text_embd,
+                                const int32_t* text_lengths, int B, int T_text, float* pred_lengths, void* stream) {
+  API_BEGIN
+  Ctx c = make_ctx(h, params, nullptr, nullptr, 0, stream);
+  length_predictor_fwd(c, text_embd, text_lengths, B, T_text, pred_lengths);
+  API_END
+}
+
+int vaenar_prior_sample(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
+                        const float* text_embd, const int32_t* text_lengths, const int32_t* z_lengths, int B,
+                        int T_text, int T_z, float* z_io, float* logp, void* stream) {
+  API_BEGIN
+  Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
+  prior_sample(c, text_embd, text_lengths, z_lengths, B, T_text, T_z, z_io, logp);
+  API_END
+}
+
+int vaenar_prior_log_probability(vaenar_handle_t h, const float* params, const void* packed, void* ws,
+                                 int64_t ws_bytes, const float* z, const float* text_embd,
+                                 const int32_t* text_lengths, const int32_t* z_lengths, int B, int T_text, int T_z,
+                                 float* logp, void* stream) {
+  API_BEGIN
+  Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
+  prior_logprob(c, z, text_embd, text_lengths, z_lengths, B, T_text, T_z, logp);
+  API_END
+}
+
+int vaenar_posterior_fwd(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
+                         const float* mels, const float* text_embd, const int32_t* text_lengths,
+                         const int32_t* z_lengths, const float* eps, int B, int T_text, int T_mel, int T_z, int rf,
+                         float* z, float* logq, void* stream) {
+  API_BEGIN
+  Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
+  posterior_fwd(c, mels, text_embd, text_lengths, z_lengths, eps, B, T_text, T_mel, T_z, rf, z, logq);
+  API_END
+}
+
+int vaenar_decoder_fwd(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
+                       const float* z, const float* text_embd, const int32_t* z_lengths,
+                       const int32_t* text_lengths, int B, int T_text, int T_z, int rf, float* initial_mel,
+                       float* mel, float* alignments, void* stream) {
+  API_BEGIN
+  Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
+  decoder_fwd(c, z, text_embd, z_lengths, text_lengths, B, T_text, T_z, rf, initial_mel, mel, alignments);
+  API_END
+}
+
+int vaenar_inference(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
+                     const int32_t* texts, const int32_t* text_lengths, const int32_t* z_lengths, int B, int T_text,
+                     int T_z, int rf, float* z_io, float* text_embd, float* mel, float* alignments, float* logp,
+                     void* stream) {
+  API_BEGIN
+  Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
+  inference_fwd(c, texts, text_lengths, z_lengths, B, T_text, T_z, rf, z_io, text_embd, mel, alignments, logp);
+  API_END
+}
+
+int vaenar_elbo_fwd(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
+                    const int32_t* texts, const float* mels, const int32_t* mel_lengths,
+                    const int32_t* text_lengths, const int32_t* z_lengths, const float* eps, int B, int T_text,
+                    int T_mel, int T_z, int rf, float* mel_out, float* l2, float* kl, float* length_loss,
+                    float* alignments, void* stream) {
+  API_BEGIN
+  Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
+  elbo_fwd(c, texts, mels, mel_lengths, text_lengths, z_lengths, eps, B, T_text, T_mel, T_z, rf, mel_out, l2, kl,
+           length_loss, alignments);
+  API_END
+}
+
+int vaenar_randn(float* out, int64_t n, uint64_t seed, uint64_t stream_id, float stddev, void* stream) {
+  API_BEGIN
+  const int64_t thr = (n + 3) / 4;
+  randn_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, seed,
+                                                                                                    stream_id, stddev);
+  check_launch("randn");
+  API_END
+}
+
+long vaenar_launch_count(void) { return g_launch_count; }
+
+// Enable (1) / disable (0) per-launch CUDA-event timing of the tensor-core kernels.  Not for use during
+// graph capture.  vaenar_profile_report() synchronises the device and returns a JSON object
+// {class: {launches, ms, flops, bytes}} for the launches seen since the last enable.
+int vaenar_profile_enable(int on) {
+  if (on) {
+    for (auto& kv : g_stats)
+      for (auto& ev : kv.second.events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    g_stats.clear();
+  }
+  g_profile = on != 0;
+  return 0;
+}
+const char* vaenar_profile_report(void) {
+  cudaDeviceSynchronize();
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : g_stats) {
+    double ms = 0;
+    for (auto& ev : kv.second.events) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, ev.first, ev.second) == cudaSuccess) ms += t;
+    }
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+             first ? "" : ", ", kv.first.c_str(), kv.second.launches, ms, kv.second.flops, kv.second.bytes);
+    out += buf;
+    first = false;
+  }
+  out += "}";
+  g_profile_json = out;
+  return g_profile_json.c_str();
+}
+
+// ---------------------------------------------------------------------------- block-level test hooks
+struct TestCtx : Ctx {
+  vaenar_model dummy;
+};
+static void test_ctx(TestCtx& c, void* ws, int64_t ws_bytes, void* stream) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) VB_THROW("no CUDA device: the B200 path has no CPU fallback");
+  set_attrs(nullptr);
+  c.m = &c.dummy; c.params = nullptr; c.packed = nullptr;
+  c.ws = static_cast<uint8_t*>(ws); c.ws_bytes = ws_bytes; c.stream = static_cast<cudaStream_t>(stream);
+}
+static void launch_pack(Ctx& c, const std::vector<PackOp>& ops, PackOp* dev_ops) {
+  VB_CUDA(cudaMemcpyAsync(dev_ops, ops.data(), ops.size() * sizeof(PackOp), cudaMemcpyHostToDevice, c.stream));
+  int maxK = 0, maxN = 0;
+  for (auto& o : ops) { maxK = std::max(maxK, o.K); maxN = std::max(maxN, o.N); }
+  dim3 grid(cdiv(maxN, 32), cdiv(maxK, 32), static_cast<unsigned>(ops.size()));
+  pack_weights_kernel<<<grid, dim3(32, 8), 0, c.stream>>>(dev_ops);
+  check_launch("pack_weights(test)");
+}
+// hi/lo fp16 split of an fp32 activation matrix (test-only producer; the model's epilogues emit these directly)
+__global__ void split_f16_kernel(const float* in, __half* hi, __half* lo, long n) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const __half h = __float2half_rn(in[i]);
+    hi[i] = h;
+    if (lo) lo[i] = __float2half_rn(in[i] - __half2float(h));
+  }
+}
+
+int vaenar_test_dense(const float* A, const float* W, const float* bias, const float* residual, const float* gamma,
+                      const float* beta, int M, int K, int N, int act, int ln, int split, int block_n, float* out,
+                      void* ws, int64_t ws_bytes, void* stream) {
+  API_BEGIN
+  TestCtx c;
+  test_ctx(c, ws, ws_bytes, stream);
+  const int Kp = kpad64(K), parts = split ? 3 : 1;
+  __half* Ah = c.alloc<__half>(static_cast<int64_t>(M) * K);
+  __half* Al = c.alloc<__half>(static_cast<int64_t>(M) * K);
+  __half* Wp = c.alloc<__half>(static_cast<int64_t>(N) * parts * Kp);
+  PackOp* dops = c.alloc<PackOp>(4);
+  VB_CUDA(cudaMemsetAsync(Wp, 0, static_cast<int64_t>(N) * parts * Kp * 2, c.stream));
+  std::vector<PackOp> ops;
+  for (int p = 0; p < parts; ++p) ops.push_back(PackOp{W, Wp + p * Kp, K, N, N, parts * Kp, (split && p == 2) ? 1 : 0});
+  launch_pack(c, ops, dops);
+  const long n = static_cast<long>(M) * K;
+  split_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(A, Ah, split ? Al : nullptr, n);
+  check_launch("split");
+  GemmParams p = gp();
+  p.mode = ln ? EPI_LN : EPI_PLAIN; p.N = N; p.act = act; p.bias = bias; p.residual = residual; p.res_ld = N;
+  p.ln_gamma = gamma; p.ln_beta = beta; p.out_f32 = out; p.ld_f32 = N;
+  p.nseg = parts;
+  for (int q = 0; q < parts; ++q) { p.seg_map[q] = (q == 1) ? 1 : 0; p.seg_shift[q] = 0; p.seg_kblocks[q] = Kp / 64; }
+  run_gemm(c, block_n, AOp{Ah, K, K}, AOp{split ? Al : nullptr, K, K}, 1, M, Wp, parts * Kp, N, p);
+  API_END
+}
+
+int vaenar_test_conv1d(const float* X, const float* W, const float* bias, int B, int T, int Cin, int Cout, int taps,
+                       int act, int split, float* out, void* ws, int64_t ws_bytes, void* stream) {
+  API_BEGIN
+  TestCtx c;
+  test_ctx(c, ws, ws_bytes, stream);
+  const int cp = kpad64(Cin), parts = split ? 3 : 1, Ktot = taps * parts * cp;
+  if (taps * parts > kMaxSegs) VB_THROW("too many segments");
+  const long n = static_cast<long>(B) * T * Cin;
+  __half* Xh = c.alloc<__half>(n);
+  __half* Xl = c.alloc<__half>(n);
+  __half* Wp = c.alloc<__half>(static_cast<int64_t>(Cout) * Ktot);
+  PackOp* dops = c.alloc<PackOp>(taps * parts);
+  VB_CUDA(cudaMemsetAsync(Wp, 0, static_cast<int64_t>(Cout) * Ktot * 2, c.stream));
+  std::vector<PackOp> ops;
+  for (int j = 0; j < taps; ++j)
+    for (int p = 0; p < parts; ++p)
+      ops.push_back(PackOp{W + static_cast<long>(j) * Cin * Cout, Wp + (j * parts + p) * cp, Cin, Cout, Cout, Ktot,
+                           (split && p == 2) ? 1 : 0});
+  launch_pack(c, ops, dops);
+  split_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(X, Xh, split ? Xl : nullptr, n);
+  check_launch("split");
+  GemmParams p = gp();
+  p.mode = EPI_PLAIN; p.N = Cout; p.act = act; p.bias = bias; p.out_f32 = out; p.ld_f32 = Cout;
+  segs_conv(p, taps, Cin, split != 0);
+  run_gemm(c, 128, AOp{Xh, Cin, Cin}, AOp{split ? Xl : nullptr, Cin, Cin}, B, T, Wp, Ktot, Cout, p);
+  API_END
+}
+
+// [B, T, H*64] fp32 -> V^T fp16 [B*H*64, tpad]
+__global__ void vt_transpose_kernel(const float* v, __half* vt, int B, int T, int H, int tpad) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long n = static_cast<long>(B) * T * H * 64;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % (H * 64));
+  const long bt = i / (H * 64);
+  const int t = static_cast<int>(bt % T), b = static_cast<int>(bt / T);
+  vt[(static_cast<long>(b) * H * 64 + c) * tpad + t] = __float2half_rn(v[i]);
+}
+__global__ void half_to_float_kernel(const __half* in, float* out, long n) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __half2float(in[i]);
+}
+
+int vaenar_test_attention(const float* q, const float* k, const float* v, const int32_t* q_len,
+                          const int32_t* k_len, int B, int H, int Tq, int Tk, int causal, float* ctx, float* ali,
+                          void* ws, int64_t ws_bytes, void* stream) {
+  API_BEGIN
+  TestCtx c;
+  test_ctx(c, ws, ws_bytes, stream);
+  const int D = H * 64, tpad = vt_pad(Tk);
+  __half* qh = c.alloc<__half>(static_cast<int64_t>(B) * Tq * D);
+  __half* kh = c.alloc<__half>(static_cast<int64_t>(B) * Tk * D);
+  __half* vt = c.alloc<__half>(static_cast<int64_t>(B) * D * tpad);
+  __half* ch = c.alloc<__half>(static_cast<int64_t>(B) * Tq * D);
+  run_cast(c, q, qh, static_cast<int64_t>(B) * Tq * D);
+  run_cast(c, k, kh, static_cast<int64_t>(B) * Tk * D);
+  const long nv = static_cast<long>(B) * Tk * D;
+  VB_CUDA(cudaMemsetAsync(vt, 0xFF, static_cast<int64_t>(B) * D * tpad * 2, c.stream));   // NaN padding: must never leak
+  vt_transpose_kernel<<<static_cast<unsigned>((nv + 255) / 256), 256, 0, c.stream>>>(v, vt, B, Tk, H, tpad);
+  check_launch("vt_transpose");
+  run_attention(c, B, H, AttnCall{qh, D, 0, Tq, kh, D, 0, Tk, vt, static_cast<long>(B) * D, tpad, 0, q_len, k_len, causal, ch, D,
+                                  ali});
+  const long nc = static_cast<long>(B) * Tq * D;
+  half_to_float_kernel<<<static_cast<unsigned>((nc + 255) / 256), 256, 0, c.stream>>>(ch, ctx, nc);
+  check_launch("half_to_float");
+  API_END
+}
+
+}  // extern "C"

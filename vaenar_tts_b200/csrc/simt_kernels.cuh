@@ -1,0 +1,415 @@
+// Non-tensor-core kernels of the path: weight packing, embedding gather, positional-encoding table,
+// the fp32 flow linear algebra (ActNorm (+) InvertibleLinear, 128x128 LU / inverse), reductions for
+// the log-densities and losses, and a counter-based normal RNG.  All fp32 (fp64 where the reference
+// uses float64, modules/flow.py:126-129,141-144).
+#pragma once
+#include "ptx.cuh"
+
+namespace vb {
+
+// ------------------------------------------------------------------ weight packing
+// dst[n * ldd + k] = fp16( src[k * lds + n] )          (mode 0: hi part)
+//                  = fp16( src - float(fp16(src)) )    (mode 1: lo part of the split-fp16 pair)
+// Keras Dense kernels are [in, out]; the UMMA B operand wants [out, in] (K-major).
+struct PackOp {
+  const float* src;
+  __half* dst;
+  int K, N, lds, ldd, mode;
+};
+__global__ void pack_weights_kernel(const PackOp* __restrict__ ops) {
+  const PackOp op = ops[blockIdx.z];
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  if (k0 >= op.K || n0 >= op.N) return;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < op.K && n < op.N) ? op.src[static_cast<long>(k) * op.lds + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    if (n < op.N && k < op.K) {
+      const float v = tile[threadIdx.x][i];
+      const __half hi = __float2half_rn(v);
+      op.dst[static_cast<long>(n) * op.ldd + k] = op.mode ? __float2half_rn(v - __half2float(hi)) : hi;
+    }
+  }
+}
+
+// Inference-mode BatchNorm folded to a per-channel affine (modules/utils.py:72; Keras eps 1e-3):
+//   y = (x - mean) * rsqrt(var + eps) * gamma + beta  =  x * scale + shift
+__global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                               float* scale, float* shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float s = gamma[c] * rsqrtf(var[c] + eps);
+    scale[c] = s;
+    shift[c] = beta[c] - mean[c] * s;
+  }
+}
+
+__global__ void concat2_kernel(const float* a, int na, const float* b, int nb, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < na) out[i] = a[i];
+  else if (i < na + nb) out[i] = b[i - na];
+}
+
+// ------------------------------------------------------------------ elementwise helpers
+__global__ void cast_f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long n) {
+  const long i = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    uint2 u;
+    u.x = pack_half2(v.x, v.y);
+    u.y = pack_half2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + i) = u;
+  } else {
+    for (long j = i; j < n; ++j) out[j] = __float2half_rn(in[j]);
+  }
+}
+
+// Embedding lookup (modules/encoder.py:10-12,81): rows of the table as fp16 conv operands.
+__global__ void embed_kernel(const int* __restrict__ ids, const float* __restrict__ table, __half* __restrict__ out,
+                             int n_tokens, int dim, int vocab) {
+  const int tok = blockIdx.x;
+  if (tok >= n_tokens) return;
+  int id = ids[tok];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  for (int d = threadIdx.x; d < dim; d += blockDim.x)
+    out[static_cast<long>(tok) * dim + d] = __float2half_rn(table[static_cast<long>(id) * dim + d]);
+}
+
+// PositionalEncoding.positional_encoding (modules/utils.py:332-355):
+//   even d: sin(t*step / 10000^(d/D)) ; odd d: cos(t*step / 10000^((d-1)/D))
+__global__ void pe_table_kernel(float* __restrict__ out, int T, int D, float step) {
+  const int t = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float pos = static_cast<float>(t) * step;
+    float v;
+    if ((d & 1) == 0) v = sinf(pos / powf(10000.f, static_cast<float>(d) / static_cast<float>(D)));
+    else v = cosf(pos / powf(10000.f, static_cast<float>(d - 1) / static_cast<float>(D)));
+    out[static_cast<long>(t) * D + d] = v;
+  }
+}
+
+// mels[:, ::rf, :] (models/models.py:123) as fp16 GEMM operand [B, Tz, 80]
+__global__ void reduce_mels_kernel(const float* __restrict__ mels, __half* __restrict__ out, int B, int Tm, int Tz,
+                                   int rf, int C) {
+  const int row = blockIdx.x;           // b * Tz + tz
+  const int b = row / Tz, tz = row % Tz;
+  const int tm = tz * rf;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float v = tm < Tm ? mels[(static_cast<long>(b) * Tm + tm) * C + c] : 0.f;
+    out[static_cast<long>(row) * C + c] = __float2half_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------ block reduce
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float t = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) t = warp_sum(t);
+  if (threadIdx.x == 0) sh[0] = t;
+  __syncthreads();
+  return sh[0];
+}
+
+// ------------------------------------------------------------------ length predictor
+// DenseLengthPredictor.call (modules/length_predictor.py:35-42): sum_t mask * exp(x_t . w + b)
+__global__ void length_predictor_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                        const float* __restrict__ bias, const int* __restrict__ lens,
+                                        float* __restrict__ out, int T, int D) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  const int len = lens[b];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float acc = 0.f;
+  for (int t = warp; t < T && t < len; t += nw) {
+    const float* row = x + (static_cast<long>(b) * T + t) * D;
+    float dot = 0.f;
+    for (int d = lane; d < D; d += 32) dot += row[d] * w[d];
+    dot = warp_sum(dot);
+    if (lane == 0) acc += expf(dot + bias[0]);
+  }
+  const float tot = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[b] = tot;
+}
+
+// ------------------------------------------------------------------ flow linear algebra (DIM = 128)
+constexpr int FLOW_DIM = 128;
+
+// log|det W| in float64 with partial pivoting (modules/flow.py:126-129: slogdet(cast(W, float64))).
+// One CTA of 128 threads per matrix; thread j owns column j.
+__global__ void slogdet128_kernel(const float* const* __restrict__ Ws, double* __restrict__ out) {
+  extern __shared__ double A[];                    // [128][129]
+  __shared__ int piv;
+  __shared__ double pivval;
+  const float* W = Ws[blockIdx.x];
+  const int j = threadIdx.x;
+  constexpr int LD = FLOW_DIM + 1;
+  for (int i = 0; i < FLOW_DIM; ++i) A[i * LD + j] = static_cast<double>(W[i * FLOW_DIM + j]);
+  __syncthreads();
+  double logdet = 0.0;
+  for (int k = 0; k < FLOW_DIM; ++k) {
+    if (j == 0) {
+      int best = k;
+      double bv = fabs(A[k * LD + k]);
+      for (int i = k + 1; i < FLOW_DIM; ++i) {
+        const double v = fabs(A[i * LD + k]);
+        if (v > bv) { bv = v; best = i; }
+      }
+      piv = best;
+      pivval = bv;
+    }
+    __syncthreads();
+    const int pr = piv;
+    if (pr != k) {
+      const double tmp = A[k * LD + j];
+      A[k * LD + j] = A[pr * LD + j];
+      A[pr * LD + j] = tmp;
+    }
+    __syncthreads();
+    logdet += log(pivval);
+    const double pinv = 1.0 / A[k * LD + k];
+    const double akj = A[k * LD + j];
+    __syncthreads();
+    if (j > k) {
+      for (int i = k + 1; i < FLOW_DIM; ++i) A[i * LD + j] -= A[i * LD + k] * pinv * akj;
+    }
+    __syncthreads();
+  }
+  if (j == 0) out[blockIdx.x] = logdet;
+}
+
+// fp32 inverse by Gauss-Jordan with partial pivoting (modules/flow.py:139: tf.linalg.inv(self.weight)).
+// One CTA of 256 threads per matrix; thread j owns column j of the augmented [128 x 256] system.
+__global__ void inverse128_kernel(const float* const* __restrict__ Ws, float* __restrict__ out) {
+  extern __shared__ float G[];                     // [128][257] + column buffer [128]
+  __shared__ int piv;
+  const float* W = Ws[blockIdx.x];
+  float* Winv = out + static_cast<long>(blockIdx.x) * FLOW_DIM * FLOW_DIM;
+  const int j = threadIdx.x;                       // 0..255
+  constexpr int LD = 2 * FLOW_DIM + 1;
+  float* colk = G + FLOW_DIM * LD;
+  for (int i = 0; i < FLOW_DIM; ++i)
+    G[i * LD + j] = j < FLOW_DIM ? W[i * FLOW_DIM + j] : ((j - FLOW_DIM) == i ? 1.f : 0.f);
+  __syncthreads();
+  for (int k = 0; k < FLOW_DIM; ++k) {
+    if (j == 0) {
+      int best = k;
+      float bv = fabsf(G[k * LD + k]);
+      for (int i = k + 1; i < FLOW_DIM; ++i) {
+        const float v = fabsf(G[i * LD + k]);
+        if (v > bv) { bv = v; best = i; }
+      }
+      piv = best;
+    }
+    __syncthreads();
+    const int pr = piv;
+    if (pr != k) {
+      const float tmp = G[k * LD + j];
+      G[k * LD + j] = G[pr * LD + j];
+      G[pr * LD + j] = tmp;
+    }
+    __syncthreads();
+    const float pinv = 1.0f / G[k * LD + k];
+    if (j < FLOW_DIM) colk[j] = G[j * LD + k];
+    __syncthreads();
+    const float rowk = G[k * LD + j] * pinv;
+    G[k * LD + j] = rowk;
+    for (int i = 0; i < FLOW_DIM; ++i)
+      if (i != k) G[i * LD + j] -= colk[i] * rowk;
+    __syncthreads();
+  }
+  if (j >= FLOW_DIM)
+    for (int i = 0; i < FLOW_DIM; ++i) Winv[i * FLOW_DIM + (j - FLOW_DIM)] = G[i * LD + j];
+}
+
+// Fold ActNorm into the invertible linear map, both directions (modules/flow.py:123-187):
+//   forward  (sample):        y = (z * e^s + b) W            = z Mf + cf ,  Mf = diag(e^s) W , cf = b W
+//   backward (log_prob):      y = (z W^-1 - b) / (e^s + 1e-8) = z Mb + cb ,  Mb = W^-1 diag(r), cb = -b r
+// consts[step] = { sum(log_scale), log|det W| }.
+__global__ void flow_fold_kernel(const float* const* __restrict__ Ws, const float* const* __restrict__ log_scales,
+                                 const float* const* __restrict__ biases, const float* __restrict__ Winv,
+                                 const double* __restrict__ logdet64, float* __restrict__ Mf, float* __restrict__ cf,
+                                 float* __restrict__ Mb, float* __restrict__ cb, float* __restrict__ consts) {
+  __shared__ float sh[32];
+  const int s = blockIdx.x;
+  const float* W = Ws[s];
+  const float* ls = log_scales[s];
+  const float* bi = biases[s];
+  const float* Wi = Winv + static_cast<long>(s) * FLOW_DIM * FLOW_DIM;
+  const int j = threadIdx.x;   // 128 threads, column j
+  float c = 0.f;
+  for (int i = 0; i < FLOW_DIM; ++i) {
+    const float w = W[i * FLOW_DIM + j];
+    Mf[(static_cast<long>(s) * FLOW_DIM + i) * FLOW_DIM + j] = expf(ls[i]) * w;
+    c += bi[i] * w;
+  }
+  cf[s * FLOW_DIM + j] = c;
+  const float r = 1.0f / (expf(ls[j]) + 1e-8f);
+  for (int i = 0; i < FLOW_DIM; ++i) Mb[(static_cast<long>(s) * FLOW_DIM + i) * FLOW_DIM + j] = Wi[i * FLOW_DIM + j] * r;
+  cb[s * FLOW_DIM + j] = -bi[j] * r;
+  const float tot = block_sum(ls[j], sh);
+  if (j == 0) {
+    consts[2 * s] = tot;
+    consts[2 * s + 1] = static_cast<float>(logdet64[s]);
+  }
+}
+
+// y[rows,128] = x[rows,128] M[128,128] + c  in fp32 (CUDA cores; exactness matters more than speed here:
+// the flow state z carries the log-density).  In place is safe: a CTA stages its 32 rows first.
+// Also emits the fp16 copy consumed by the conditioner's pre-projection GEMM.
+__global__ void __launch_bounds__(256)
+flow_linear_kernel(float* __restrict__ z, __half* __restrict__ z_h, const float* __restrict__ M,
+                   const float* __restrict__ c, long rows) {
+  extern __shared__ float smf[];
+  float* Ms = smf;                         // [128][128]
+  float* Xs = smf + FLOW_DIM * FLOW_DIM;   // [32][128]
+  const long r0 = static_cast<long>(blockIdx.x) * 32;
+  for (int i = threadIdx.x; i < FLOW_DIM * FLOW_DIM / 4; i += 256)
+    reinterpret_cast<float4*>(Ms)[i] = reinterpret_cast<const float4*>(M)[i];
+  for (int i = threadIdx.x; i < 32 * FLOW_DIM / 4; i += 256) {
+    const long row = r0 + (i * 4) / FLOW_DIM;
+    reinterpret_cast<float4*>(Xs)[i] =
+        row < rows ? reinterpret_cast<const float4*>(z + r0 * FLOW_DIM)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 31;   // columns tx*4 .. +3
+  const int ty = threadIdx.x >> 5;   // rows ty*4 .. +3
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  for (int k = 0; k < FLOW_DIM; ++k) {
+    const float4 m = *reinterpret_cast<const float4*>(Ms + k * FLOW_DIM + tx * 4);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const float x = Xs[(ty * 4 + a) * FLOW_DIM + k];
+      acc[a][0] = fmaf(x, m.x, acc[a][0]);
+      acc[a][1] = fmaf(x, m.y, acc[a][1]);
+      acc[a][2] = fmaf(x, m.z, acc[a][2]);
+      acc[a][3] = fmaf(x, m.w, acc[a][3]);
+    }
+  }
+  const float4 cc = *reinterpret_cast<const float4*>(c + tx * 4);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const long row = r0 + ty * 4 + a;
+    if (row < rows) {
+      const float4 o = make_float4(acc[a][0] + cc.x, acc[a][1] + cc.y, acc[a][2] + cc.z, acc[a][3] + cc.w);
+      *reinterpret_cast<float4*>(z + row * FLOW_DIM + tx * 4) = o;
+      uint2 u;
+      u.x = pack_half2(o.x, o.y);
+      u.y = pack_half2(o.z, o.w);
+      *reinterpret_cast<uint2*>(z_h + row * FLOW_DIM + tx * 4) = u;
+    }
+  }
+}
+
+// Per-batch Gaussian base log-density: sum_{t < len} sum_d -0.5 (ln 2pi + e^2)   (modules/prior.py:37-41,147-151)
+__global__ void base_logprob_kernel(const float* __restrict__ e, const int* __restrict__ lens, float* __restrict__ out,
+                                    int T, int D) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  const int len = min(lens[b], T);
+  const long n = static_cast<long>(len) * D;
+  const float* base = e + static_cast<long>(b) * T * D;
+  float acc = 0.f;
+  for (long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = base[i];
+    acc += -0.5f * (1.8378770664093453f + v * v);
+  }
+  const float tot = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[b] = tot;
+}
+
+// logp[b] = base[b] + sign * ( sum_rows row_acc  +  len_b * sum_steps (sum_s + logdetW) )
+//   sample       (modules/prior.py:154-169): sign = -1, row_acc = sum of coupling forward log-dets
+//   log_prob     (modules/prior.py:119-152): row_acc already holds the (negative) backward coupling log-dets,
+//                                            the linear/actnorm terms enter with sign -1 as well.
+__global__ void prior_logp_finalize_kernel(const float* __restrict__ base, const float* __restrict__ row_acc,
+                                           const float* __restrict__ consts, int nsteps,
+                                           const int* __restrict__ lens, float* __restrict__ out, int T,
+                                           float row_sign) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  float acc = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) acc += row_acc[static_cast<long>(b) * T + t];
+  const float rows = block_sum(acc, sh);
+  if (threadIdx.x == 0) {
+    float lin = 0.f;
+    for (int s = 0; s < nsteps; ++s) lin += consts[2 * s] + consts[2 * s + 1];
+    out[b] = base[b] + row_sign * rows - static_cast<float>(lens[b]) * lin;
+  }
+}
+
+// Per-batch sum of a per-row accumulator (posterior log q, modules/posterior.py:62-71)
+__global__ void row_sum_kernel(const float* __restrict__ row_acc, float* __restrict__ out, int T) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  float acc = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) acc += row_acc[static_cast<long>(b) * T + t];
+  const float tot = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[b] = tot;
+}
+
+// VAENAR._compute_l2_loss per batch element (models/models.py:67-86, n_sample = 1):
+//   out[b] (+)= sum_{t < len} mean_d (rec - tgt)^2 / len
+__global__ void l2_loss_kernel(const float* __restrict__ rec, int rec_T, const float* __restrict__ tgt, int tgt_T,
+                               const int* __restrict__ lens, float* __restrict__ out, int D, int accumulate) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  const int len = min(lens[b], tgt_T);
+  float acc = 0.f;
+  for (long i = threadIdx.x; i < static_cast<long>(len) * D; i += blockDim.x) {
+    const int t = static_cast<int>(i / D), d = static_cast<int>(i % D);
+    const float df = rec[(static_cast<long>(b) * rec_T + t) * D + d] - tgt[(static_cast<long>(b) * tgt_T + t) * D + d];
+    acc += df * df;
+  }
+  const float tot = block_sum(acc, sh);
+  if (threadIdx.x == 0) {
+    const float v = tot / static_cast<float>(D) / static_cast<float>(lens[b]);
+    out[b] = accumulate ? out[b] + v : v;
+  }
+}
+
+// ------------------------------------------------------------------ counter-based N(0,1) generator
+// Philox4x32-10 + Box-Muller; element i of a stream is a pure function of (seed, stream, i).
+__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,
+                                             uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+  const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+__global__ void randn_kernel(float* __restrict__ out, long n, uint64_t seed, uint64_t stream, float stddev) {
+  const long i4 = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= n) return;
+  uint32_t c0 = static_cast<uint32_t>(i4), c1 = static_cast<uint32_t>(i4 >> 32);
+  uint32_t c2 = static_cast<uint32_t>(stream), c3 = static_cast<uint32_t>(stream >> 32);
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const float u0 = (static_cast<float>(c0) + 0.5f) * 2.3283064365386963e-10f;
+  const float u1 = (static_cast<float>(c1) + 0.5f) * 2.3283064365386963e-10f;
+  const float u2 = (static_cast<float>(c2) + 0.5f) * 2.3283064365386963e-10f;
+  const float u3 = (static_cast<float>(c3) + 0.5f) * 2.3283064365386963e-10f;
+  const float r0 = sqrtf(-2.f * logf(u0)), r1 = sqrtf(-2.f * logf(u2));
+  float s0, co0, s1, co1;
+  sincosf(6.283185307179586f * u1, &s0, &co0);
+  sincosf(6.283185307179586f * u3, &s1, &co1);
+  const float v[4] = {r0 * co0 * stddev, r0 * s0 * stddev, r1 * co1 * stddev, r1 * s1 * stddev};
+  for (int j = 0; j < 4 && i4 * 4 + j < n; ++j) out[i4 * 4 + j] = v[j];
+}
+
+}  // namespace vb

@@ -1,0 +1,501 @@
+"""Host-side mirror of the reference's ``models.models.VAENAR`` (models/models.py:9-226) on top of the
+C ABI of libvaenar_sm100.so.  Same constructor, method and attribute names as the Keras model so that
+train.py:114-179 / inference.py:38-72,121-143 can use it unchanged:
+
+    model = VAENAR(hps)
+    model(inputs=, mel_targets=, mel_lengths=, text_lengths=, reduction_factor=, training=, reduce_loss=)
+    model.inference(inputs=, mel_lengths=, text_lengths=, reduction_factor=)
+    model.text_encoder(t, t_l, pos_step=, training=) ; model.length_predictor(x, t_l, training=)
+    model.prior.sample(lens, text_embd, t_l, training=, temperature=) ; model.prior.log_probability(...)
+    model.decoder(z, text_embd, z_lens, t_l, training=, reduction_factor=) ; model.mel_text_len_ratio
+
+PyTorch tensors are only the device-memory containers; all arithmetic happens in the sm_100a kernels.
+There is no CPU / eager fallback: a compute call without a CUDA device (or without the built library) raises.
+"""
+import ctypes
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import _lib
+from ._lib import HParamsStruct, VaenarError, check
+
+
+def _tf(hps_section):
+    """Accept both the reference nesting (hps.Encoder.Transformer.x) and a flattened one (hps.Encoder.x)."""
+    return getattr(hps_section, "Transformer", hps_section)
+
+
+def hparams_struct(hps) -> HParamsStruct:
+    E, D, Q, R, C = _tf(hps.Encoder), _tf(hps.Decoder), _tf(hps.Posterior), _tf(hps.Prior), hps.Common
+    s = HParamsStruct()
+    s.vocab_size, s.embd_dim, s.enc_n_conv, s.enc_hidden = E.vocab_size, E.embd_dim, E.n_conv, E.pre_hidden
+    s.enc_conv_kernel, s.enc_n_blk, s.enc_att_dim, s.enc_heads, s.enc_ffn = (
+        E.conv_kernel, E.n_blk, E.attention_dim, E.attention_heads, E.ffn_hidden)
+    s.dec_nblk, s.dec_att_dim, s.dec_heads, s.dec_ffn = D.nblk, D.attention_dim, D.attention_heads, D.ffn_hidden
+    s.post_n_conv, s.post_filters, s.post_kernel = D.post_n_conv, D.post_conv_filters, D.post_conv_kernel
+    s.posterior_pre_hidden, s.posterior_nblk, s.posterior_att_dim = Q.pre_hidden, Q.nblk, Q.attention_dim
+    s.posterior_heads, s.posterior_ffn = Q.attention_heads, Q.ffn_hidden
+    s.prior_n_blk, s.prior_n_tblk, s.prior_att_dim = R.n_blk, R.n_transformer_blk, R.attention_dim
+    s.prior_heads, s.prior_ffn = R.attention_heads, R.ffn_hidden
+    s.latent_dim, s.out_dim = C.latent_dim, C.output_dim
+    s.max_reduction_factor, s.final_reduction_factor = C.max_reduction_factor, C.final_reduction_factor
+    s.mel_text_len_ratio = float(C.mel_text_len_ratio)
+    for name, temp in (("Encoder", getattr(E, "attention_temperature", 1.0)),
+                       ("Decoder", getattr(D, "attention_temperature", 1.0)),
+                       ("Posterior", getattr(Q, "temperature", 1.0)), ("Prior", getattr(R, "temperature", 1.0))):
+        if float(temp) != 1.0:
+            raise VaenarError(f"{name} attention temperature {temp} != 1.0 is not supported by the fused kernel")
+    if getattr(R, "inverse", False):
+        raise VaenarError("Prior.inverse=True is not supported (reference configs use inverse=False)")
+    return s
+
+
+class _Sub:
+    """Callable sub-module facade (Keras ``Layer.__call__`` look-alike)."""
+
+    def __init__(self, fn, **extra):
+        self._fn = fn
+        for k, v in extra.items():
+            setattr(self, k, v)
+
+    def __call__(self, *a, **kw):
+        return self._fn(*a, **kw)
+
+
+class VAENAR:
+    def __init__(self, hps, name="VAENAR", device=None, seed=None, **kwargs):
+        self.hps = hps
+        self.name = name
+        self.n_sample = hps.Train.num_samples
+        if self.n_sample != 1:
+            raise VaenarError("num_samples != 1 is not implemented (reference configs use 1)")
+        self.mel_text_len_ratio = hps.Common.mel_text_len_ratio
+        self.max_reduction_factor = hps.Common.max_reduction_factor
+        self._lib = _lib.load()
+        self._hp = hparams_struct(hps)
+        h = ctypes.c_void_p()
+        check(self._lib.vaenar_create(ctypes.byref(self._hp), ctypes.byref(h)))
+        self._h = h
+        if device is None:
+            device = "cuda" if torch.cuda.is_available() else "cpu"
+        self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        # ---- parameter manifest: one flat fp32 buffer, named views into it
+        L = self._lib
+        self._manifest = []
+        for i in range(L.vaenar_num_params(h)):
+            nd = L.vaenar_param_ndim(h, i)
+            shape = tuple(int(L.vaenar_param_dim(h, i, d)) for d in range(nd))
+            self._manifest.append((L.vaenar_param_name(h, i).decode(), shape, int(L.vaenar_param_offset(h, i)),
+                                   bool(L.vaenar_param_trainable(h, i))))
+        self._flat = torch.zeros(int(L.vaenar_param_floats(h)), dtype=torch.float32, device=self.device)
+        self._views = OrderedDict()
+        for n, shape, off, _ in self._manifest:
+            numel = int(math.prod(shape))
+            self._views[n] = self._flat[off:off + numel].view(shape)
+        self._packed = None
+        self._dirty = True
+        self._ws = None
+        self._noise_calls = 0
+        self._seed = int(hps.Train.random_seed if seed is None else seed)
+        self.reset_parameters(self._seed)
+        # ---- sub-modules with the reference's attribute names (inference.py:59-72,129-143)
+        self.text_encoder = _Sub(self._text_encoder)
+        self.length_predictor = _Sub(self._length_predictor)
+        self.decoder = _Sub(self._decoder)
+        self.posterior = _Sub(self._posterior)
+        self.prior = _Sub(self._prior_sample, sample=self._prior_sample, log_probability=self._prior_log_probability,
+                          init=self._prior_init)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.vaenar_destroy(self._h)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ parameters
+    def reset_parameters(self, seed):
+        """Keras default initialisers (glorot_uniform Dense/Conv1D, U(-.05,.05) Embedding, zero-init
+        projections of modules/posterior.py:108-113 & modules/transform.py:12-17, QR-orthogonal
+        InvertibleLinear of modules/flow.py:120, N(0,.05) ActNorm log-scale of :160-162)."""
+        g = torch.Generator().manual_seed(int(seed))
+        sd = {}
+        for n, shape, _, _ in self._manifest:
+            if n.endswith((".bias", ".beta", ".moving_mean", ".actnorm.bias")):
+                v = torch.zeros(shape)
+            elif n.endswith((".gamma", ".moving_variance", "pos_weight")):
+                v = torch.ones(shape)
+            elif n.endswith("embeddings"):
+                v = torch.rand(shape, generator=g) * 0.1 - 0.05
+            elif n.endswith("actnorm.log_scale"):
+                v = torch.randn(shape, generator=g) * 0.05
+            elif n.endswith("linear.weight"):
+                v = torch.linalg.qr(torch.randn(shape, generator=g, dtype=torch.float64))[0].float()
+            elif any(n.endswith(s + ".kernel") for s in ("mu_projection", "logvar_projection", "log_scale_proj",
+                                                          "shift_proj")):
+                v = torch.zeros(shape)
+            elif n.endswith(".kernel"):
+                if len(shape) == 3:
+                    fan_in, fan_out = shape[0] * shape[1], shape[0] * shape[2]
+                else:
+                    fan_in, fan_out = shape
+                lim = math.sqrt(6.0 / (fan_in + fan_out))
+                v = (torch.rand(shape, generator=g) * 2 - 1) * lim
+            else:
+                raise VaenarError(f"no initialiser for {n}")
+            sd[n] = v
+        self.load_state_dict(sd)
+
+    def state_dict(self):
+        return OrderedDict((n, v.detach().clone()) for n, v in self._views.items())
+
+    def load_state_dict(self, sd, strict=True):
+        missing = [n for n in self._views if n not in sd]
+        extra = [n for n in sd if n not in self._views]
+        if strict and (missing or extra):
+            raise VaenarError(f"state dict mismatch: missing {missing[:5]} unexpected {extra[:5]}")
+        with torch.no_grad():
+            for n, v in self._views.items():
+                if n in sd:
+                    src = torch.as_tensor(sd[n], dtype=torch.float32)
+                    if src.numel() != v.numel():
+                        raise VaenarError(f"{n}: expected {tuple(v.shape)}, got {tuple(src.shape)}")
+                    v.copy_(src.reshape(v.shape))
+        self._dirty = True
+
+    @property
+    def trainable_variables(self):
+        return [self._views[n] for n, _, _, tr in self._manifest if tr]
+
+    @property
+    def variables(self):
+        return list(self._views.values())
+
+    def parameter_names(self):
+        return [n for n, _, _, _ in self._manifest]
+
+    def mark_weights_changed(self):
+        self._dirty = True
+
+    # ------------------------------------------------------------------ plumbing
+    def _require_cuda(self):
+        if self.device.type != "cuda":
+            raise VaenarError("VAENAR compute needs a CUDA device (sm_100a); there is no CPU fallback")
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+    def _i32(self, t):
+        return torch.as_tensor(t).to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
+
+    def _f32(self, t):
+        return torch.as_tensor(t).to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+
+    def _prepare(self, B, Tt, Tz, rf):
+        self._require_cuda()
+        if self._packed is None:
+            self._packed = torch.empty(int(self._lib.vaenar_packed_bytes(self._h)), dtype=torch.uint8,
+                                       device=self.device)
+        if self._dirty:
+            check(self._lib.vaenar_pack_weights(self._h, self._p(self._flat), self._p(self._packed), self._stream()))
+            self._dirty = False
+        need = int(self._lib.vaenar_workspace_bytes(self._h, B, Tt, Tz, rf))
+        if need < 0:
+            check(-1)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+
+    def _noise(self, shape, stddev=1.0):
+        out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        self._noise_calls += 1
+        check(self._lib.vaenar_randn(self._p(out), out.numel(), self._seed, self._noise_calls, float(stddev),
+                                     self._stream()))
+        return out
+
+    @staticmethod
+    def _no_training(training, what):
+        if training:
+            raise NotImplementedError(
+                f"{what}(training=True): dropout / batch-statistics BatchNorm and the backward pass are not "
+                "implemented on the CUDA path yet; refusing to silently run inference-mode arithmetic")
+
+    @staticmethod
+    def _max_len(lengths):
+        return int(torch.as_tensor(lengths).max().item())
+
+    # ------------------------------------------------------------------ sub-modules
+    def _text_encoder(self, inputs, input_lengths=None, pos_step=1.0, training=None):
+        """TransformerEncoder.call (modules/encoder.py:79-93)."""
+        self._no_training(training, "text_encoder")
+        texts = self._i32(inputs)
+        B, Tt = texts.shape
+        t_len = self._i32(input_lengths) if input_lengths is not None else torch.full((B,), Tt, dtype=torch.int32,
+                                                                                     device=self.device)
+        self._prepare(B, Tt, 1, 1)
+        out = torch.empty(B, Tt, self._hp.enc_hidden, dtype=torch.float32, device=self.device)
+        check(self._lib.vaenar_text_encoder_fwd(self._h, self._p(self._flat), self._p(self._packed), self._p(self._ws),
+                                                self._ws.numel(), self._p(texts), self._p(t_len), B, Tt,
+                                                float(pos_step), self._p(out), self._stream()))
+        return out
+
+    def _length_predictor(self, inputs, input_lengths, training=None):
+        """DenseLengthPredictor.call (modules/length_predictor.py:35-42)."""
+        self._require_cuda()
+        x = self._f32(inputs)
+        B, Tt, _ = x.shape
+        t_len = self._i32(input_lengths)
+        out = torch.empty(B, dtype=torch.float32, device=self.device)
+        check(self._lib.vaenar_length_predictor_fwd(self._h, self._p(self._flat), self._p(x), self._p(t_len), B, Tt,
+                                                    self._p(out), self._stream()))
+        return out
+
+    def _prior_sample(self, targets_lengths, condition_inputs, condition_lengths=None, training=None,
+                      temperature=1.0, epsilon=None):
+        """TransformerPrior.sample (modules/prior.py:154-169).  ``epsilon`` (optional) injects the N(0,1)
+        draw of _initial_sample (prior.py:35) for parity tests; it is scaled by ``temperature``."""
+        emb = self._f32(condition_inputs)
+        B, Tt, _ = emb.shape
+        Tz = self._max_len(targets_lengths)
+        z_len = self._i32(targets_lengths)
+        t_len = self._i32(condition_lengths)
+        self._prepare(B, Tt, Tz, 1)
+        L = self._hp.latent_dim
+        if epsilon is None:
+            z = self._noise((B, Tz, L), temperature)
+        else:
+            z = (self._f32(epsilon) * float(temperature)).contiguous().clone()
+            if tuple(z.shape) != (B, Tz, L):
+                raise VaenarError(f"epsilon shape {tuple(z.shape)} != {(B, Tz, L)}")
+        logp = torch.empty(B, dtype=torch.float32, device=self.device)
+        check(self._lib.vaenar_prior_sample(self._h, self._p(self._flat), self._p(self._packed), self._p(self._ws),
+                                            self._ws.numel(), self._p(emb), self._p(t_len), self._p(z_len), B, Tt, Tz,
+                                            self._p(z), self._p(logp), self._stream()))
+        return z, logp
+
+    def _prior_log_probability(self, z, condition_inputs, z_lengths=None, condition_lengths=None, training=None):
+        """TransformerPrior.log_probability (modules/prior.py:119-152)."""
+        z = self._f32(z)
+        emb = self._f32(condition_inputs)
+        B, Tz, _ = z.shape
+        Tt = emb.shape[1]
+        z_len = self._i32(z_lengths)
+        t_len = self._i32(condition_lengths)
+        self._prepare(B, Tt, Tz, 1)
+        logp = torch.empty(B, dtype=torch.float32, device=self.device)
+        check(self._lib.vaenar_prior_log_probability(self._h, self._p(self._flat), self._p(self._packed),
+                                                     self._p(self._ws), self._ws.numel(), self._p(z), self._p(emb),
+                                                     self._p(t_len), self._p(z_len), B, Tt, Tz, self._p(logp),
+                                                     self._stream()))
+        return logp
+
+    def _prior_init(self, *a, **kw):
+        raise NotImplementedError("prior.init (data-dependent ActNorm initialisation, modules/prior.py:171-186) "
+                                  "belongs to the training path, which is not implemented on the CUDA path yet")
+
+    def _posterior(self, inputs, src_enc, src_lengths=None, target_lengths=None, training=None, eps=None,
+                   reduction_factor=None, full_mels=None):
+        """TransformerPosterior.call fused with reparameterize + log_probability
+        (modules/posterior.py:20-72,115-130): ``inputs`` are the reduced mels [B,T_z,80]; returns (z, logq)."""
+        self._no_training(training, "posterior")
+        rm = self._f32(inputs)
+        emb = self._f32(src_enc)
+        B, Tz, _ = rm.shape
+        Tt = emb.shape[1]
+        z_len = self._i32(target_lengths)
+        t_len = self._i32(src_lengths)
+        L = self._hp.latent_dim
+        e = self._noise((B, Tz, L)) if eps is None else self._f32(eps).reshape(B, Tz, L).contiguous()
+        self._prepare(B, Tt, Tz, 1)
+        z = torch.empty(B, Tz, L, dtype=torch.float32, device=self.device)
+        logq = torch.empty(B, dtype=torch.float32, device=self.device)
+        check(self._lib.vaenar_posterior_fwd(self._h, self._p(self._flat), self._p(self._packed), self._p(self._ws),
+                                             self._ws.numel(), self._p(rm), self._p(emb), self._p(t_len),
+                                             self._p(z_len), self._p(e), B, Tt, Tz, Tz, 1, self._p(z), self._p(logq),
+                                             self._stream()))
+        return z, logq
+
+    def _decoder(self, inputs, text_embd, z_lengths=None, text_lengths=None, reduction_factor=2, training=None,
+                 return_alignments=True):
+        """TransformerDecoder.call (modules/decoder.py:181-199) -> (initial_outs, outputs, alignments)."""
+        self._no_training(training, "decoder")
+        z = self._f32(inputs)
+        emb = self._f32(text_embd)
+        B, Tz, _ = z.shape
+        Tt = emb.shape[1]
+        rf = int(reduction_factor)
+        z_len = self._i32(z_lengths)
+        t_len = self._i32(text_lengths)
+        self._prepare(B, Tt, Tz, rf)
+        O, H, nb = self._hp.out_dim, self._hp.dec_heads, self._hp.dec_nblk
+        initial = torch.empty(B, Tz * rf, O, dtype=torch.float32, device=self.device)
+        mel = torch.empty_like(initial)
+        ali = torch.empty(nb, B, H, Tz, Tt, dtype=torch.float32, device=self.device) if return_alignments else None
+        check(self._lib.vaenar_decoder_fwd(self._h, self._p(self._flat), self._p(self._packed), self._p(self._ws),
+                                           self._ws.numel(), self._p(z), self._p(emb), self._p(z_len), self._p(t_len),
+                                           B, Tt, Tz, rf, self._p(initial), self._p(mel), self._p(ali),
+                                           self._stream()))
+        return initial, mel, self._ali_dict(ali)
+
+    def _ali_dict(self, ali):
+        if ali is None:
+            return {}
+        return {f"decoder-attention-{i}": ali[i] for i in range(ali.shape[0])}
+
+    # ------------------------------------------------------------------ model API (models/models.py)
+    def inference(self, inputs, mel_lengths, text_lengths=None, reduction_factor=2, epsilon=None,
+                  return_alignments=True):
+        """VAENAR.inference (models/models.py:199-210) -> (predicted_mel, dec_alignments)."""
+        rf = int(reduction_factor)
+        texts = self._i32(inputs)
+        B, Tt = texts.shape
+        m_len = torch.as_tensor(mel_lengths)
+        z_len_host = (m_len.to(torch.int64) + rf - 1) // rf
+        Tz = self._max_len(z_len_host)
+        z_len = self._i32(z_len_host)
+        t_len = self._i32(text_lengths)
+        self._prepare(B, Tt, Tz, rf)
+        L, O, H, nb, E = (self._hp.latent_dim, self._hp.out_dim, self._hp.dec_heads, self._hp.dec_nblk,
+                          self._hp.enc_hidden)
+        z = self._noise((B, Tz, L)) if epsilon is None else self._f32(epsilon).contiguous().clone()
+        if tuple(z.shape) != (B, Tz, L):
+            raise VaenarError(f"epsilon shape {tuple(z.shape)} != {(B, Tz, L)}")
+        emb = torch.empty(B, Tt, E, dtype=torch.float32, device=self.device)
+        mel = torch.empty(B, Tz * rf, O, dtype=torch.float32, device=self.device)
+        ali = torch.empty(nb, B, H, Tz, Tt, dtype=torch.float32, device=self.device) if return_alignments else None
+        logp = torch.empty(B, dtype=torch.float32, device=self.device)
+        check(self._lib.vaenar_inference(self._h, self._p(self._flat), self._p(self._packed), self._p(self._ws),
+                                         self._ws.numel(), self._p(texts), self._p(t_len), self._p(z_len), B, Tt, Tz,
+                                         rf, self._p(z), self._p(emb), self._p(mel), self._p(ali), self._p(logp),
+                                         self._stream()))
+        self._last = dict(z=z, text_embd=emb, logp=logp)
+        return mel, self._ali_dict(ali)
+
+    def call(self, inputs, mel_targets, mel_lengths, text_lengths=None, reduction_factor=2, training=None,
+             reduce_loss=None, eps=None, return_alignments=True):
+        """VAENAR.call (models/models.py:105-197) -> (decoded_outs, l2_loss, kl_divergence, length_loss,
+        dec_alignments).  ``eps`` (optional) injects the posterior noise [B,1,T_z,latent] for parity tests."""
+        self._no_training(training, "VAENAR.call")
+        rf = int(reduction_factor)
+        texts = self._i32(inputs)
+        mels = self._f32(mel_targets)
+        B, Tt = texts.shape
+        Tm = mels.shape[1]
+        Tz = (Tm + rf - 1) // rf
+        m_len = self._i32(mel_lengths)
+        t_len = self._i32(text_lengths)
+        z_len = (m_len + (rf - 1)) // rf
+        self._prepare(B, Tt, Tz, rf)
+        L, O, H, nb = self._hp.latent_dim, self._hp.out_dim, self._hp.dec_heads, self._hp.dec_nblk
+        e = self._noise((B, Tz, L)) if eps is None else self._f32(eps).reshape(B, Tz, L).contiguous()
+        mel = torch.empty(B, Tm, O, dtype=torch.float32, device=self.device)
+        l2 = torch.empty(B, dtype=torch.float32, device=self.device)
+        kl = torch.empty_like(l2)
+        ll = torch.empty_like(l2)
+        ali = torch.empty(nb, B, H, Tz, Tt, dtype=torch.float32, device=self.device) if return_alignments else None
+        check(self._lib.vaenar_elbo_fwd(self._h, self._p(self._flat), self._p(self._packed), self._p(self._ws),
+                                        self._ws.numel(), self._p(texts), self._p(mels), self._p(m_len), self._p(t_len),
+                                        self._p(z_len), self._p(e), B, Tt, Tm, Tz, rf, self._p(mel), self._p(l2),
+                                        self._p(kl), self._p(ll), self._p(ali), self._stream()))
+        if reduce_loss:
+            l2, kl, ll = l2.mean(), kl.mean(), ll.mean()
+        return mel, l2, kl, ll, self._ali_dict(ali)
+
+    __call__ = call
+
+    def init(self, text_inputs, mel_lengths, text_lengths=None):
+        raise NotImplementedError("VAENAR.init (models/models.py:212-226) belongs to the training path, which is "
+                                  "not implemented on the CUDA path yet")
+
+
+class InferenceSession:
+    """VAENAR.inference for a fixed (B, T_text, T_z, rf) captured once into a CUDA graph: the steady-state
+    serving call is  pinned-host -> device copies, one graph launch, device -> pinned-host copy of the mel."""
+
+    def __init__(self, model: VAENAR, B, T_text, T_z, rf=2, return_alignments=False, seed=0):
+        model._require_cuda()
+        self.m, self.B, self.Tt, self.Tz, self.rf = model, B, T_text, T_z, rf
+        dev = model.device
+        hp = model._hp
+        self.texts = torch.zeros(B, T_text, dtype=torch.int32, device=dev)
+        self.t_len = torch.ones(B, dtype=torch.int32, device=dev)
+        self.z_len = torch.ones(B, dtype=torch.int32, device=dev)
+        self.eps = torch.zeros(B, T_z, hp.latent_dim, dtype=torch.float32, device=dev)
+        self.z = torch.empty_like(self.eps)
+        self.emb = torch.empty(B, T_text, hp.enc_hidden, dtype=torch.float32, device=dev)
+        self.mel = torch.empty(B, T_z * rf, hp.out_dim, dtype=torch.float32, device=dev)
+        self.logp = torch.empty(B, dtype=torch.float32, device=dev)
+        self.ali = (torch.empty(hp.dec_nblk, B, hp.dec_heads, T_z, T_text, dtype=torch.float32, device=dev)
+                    if return_alignments else None)
+        self.seed = seed
+        self.calls = 0
+        model._prepare(B, T_text, T_z, rf)
+        self.h_texts = torch.zeros(B, T_text, dtype=torch.int32).pin_memory()
+        self.h_t_len = torch.ones(B, dtype=torch.int32).pin_memory()
+        self.h_z_len = torch.ones(B, dtype=torch.int32).pin_memory()
+        self.h_mel = torch.empty(B, T_z * rf, hp.out_dim, dtype=torch.float32).pin_memory()
+        self.graph = None
+        self.launches_per_call = None
+
+    def _launch(self):
+        m = self.m
+        self.z.copy_(self.eps)
+        check(m._lib.vaenar_inference(m._h, m._p(m._flat), m._p(m._packed), m._p(m._ws), m._ws.numel(),
+                                      m._p(self.texts), m._p(self.t_len), m._p(self.z_len), self.B, self.Tt, self.Tz,
+                                      self.rf, m._p(self.z), m._p(self.emb), m._p(self.mel), m._p(self.ali),
+                                      m._p(self.logp), m._stream()))
+
+    def capture(self):
+        s = torch.cuda.Stream(self.m.device)
+        s.wait_stream(torch.cuda.current_stream(self.m.device))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._launch()
+        torch.cuda.current_stream(self.m.device).wait_stream(s)
+        torch.cuda.synchronize(self.m.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._launch()
+        return self
+
+    def set_inputs(self, texts, text_lengths, mel_lengths):
+        """Host-side staging into pinned buffers (outside the device timeline)."""
+        self.h_texts.copy_(torch.as_tensor(texts, dtype=torch.int32))
+        self.h_t_len.copy_(torch.as_tensor(text_lengths, dtype=torch.int32))
+        self.h_z_len.copy_(((torch.as_tensor(mel_lengths).to(torch.int64) + self.rf - 1) // self.rf).to(torch.int32))
+
+    def run_device(self, new_noise=True):
+        """Device-resident step: fresh noise + one graph launch (inputs already in HBM)."""
+        if new_noise:
+            self.calls += 1
+            check(self.m._lib.vaenar_randn(self.m._p(self.eps), self.eps.numel(), self.seed, self.calls, 1.0,
+                                           self.m._stream()))
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._launch()
+        return self.mel
+
+    def run_e2e(self, new_noise=True):
+        """Serving step: H2D of the pinned inputs, the graph, D2H of the mel into pinned host memory."""
+        self.texts.copy_(self.h_texts, non_blocking=True)
+        self.t_len.copy_(self.h_t_len, non_blocking=True)
+        self.z_len.copy_(self.h_z_len, non_blocking=True)
+        self.run_device(new_noise)
+        self.h_mel.copy_(self.mel, non_blocking=True)
+        return self.h_mel
+
+    @property
+    def h2d_bytes(self):
+        return self.h_texts.numel() * 4 + self.h_t_len.numel() * 4 + self.h_z_len.numel() * 4
+
+    @property
+    def d2h_bytes(self):
+        return self.h_mel.numel() * 4
