@@ -16,13 +16,17 @@
 //           A-operand layout), O += P V accumulated in TMEM; ctx = O / l.
 // No online rescaling of O is ever needed, the whole row never has to be resident, and Tk is unbounded.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 softmax (thread == row).
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 softmax: two warps per TMEM lane
+// quadrant, each owning one 64-key panel of every 128-key block (row statistics combined through shared memory).
+// Key blocks that cannot contribute are skipped: above the causal diagonal, or beyond key_len, unless the query
+// tile contains fully masked rows (which attend uniformly to ALL keys).
 #pragma once
 #include "ptx.cuh"
 
 namespace vb {
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;
+constexpr int ATT_SOFTMAX_THREADS = 256;
 constexpr int ATT_BQ = 128;     // queries per CTA
 constexpr int ATT_BK = 128;     // keys per block
 constexpr int ATT_D = 64;       // head dim
@@ -30,7 +34,7 @@ constexpr int ATT_QBYTES = ATT_BQ * ATT_D * 2;       // 16 KB
 constexpr int ATT_KBYTES = ATT_BK * ATT_D * 2;       // 16 KB
 constexpr int ATT_VBYTES = ATT_D * ATT_BK * 2;       // 16 KB (two 64-key panels of 8 KB)
 constexpr int ATT_PBYTES = ATT_BQ * ATT_BK * 2;      // 32 KB (two 64-key panels of 16 KB)
-constexpr int ATT_SMEM = ATT_QBYTES + 2 * ATT_KBYTES + 2 * ATT_VBYTES + 2 * ATT_PBYTES + 1024 + 256;
+constexpr int ATT_SMEM = ATT_QBYTES + 2 * ATT_KBYTES + 2 * ATT_VBYTES + 2 * ATT_PBYTES + 256 + 3 * 2 * ATT_BQ * 4 + 1024;
 
 struct AttnParams {
   int B, H, Tq, Tk;
@@ -50,8 +54,8 @@ template <bool kWriteAli>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // stays in the shared address space
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + ATT_QBYTES;
   uint8_t* sV = sK + 2 * ATT_KBYTES;
@@ -68,13 +72,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* p_empty = bars + 15;  // [2]
   uint64_t* o_full = bars + 17;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  float* red = reinterpret_cast<float*>(bars + 32);   // [3][2][128] row-statistic exchange between the two column halves
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * ATT_BQ;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
-  const int nblk = (p.Tk + ATT_BK - 1) / ATT_BK;
+  const int qlen = __ldg(p.q_len + b);
+  const int klen = __ldg(p.k_len + b);
+  // key blocks that can contribute to this query tile (identical in every warp role)
+  int nblk = (p.Tk + ATT_BK - 1) / ATT_BK;
+  {
+    const int q_hi = min(q0 + ATT_BQ, p.Tq);
+    const bool has_dead_rows = max(q0, qlen) < q_hi || klen <= 0;   // fully masked rows need all Tk keys
+    if (!has_dead_rows) {
+      nblk = min(nblk, (klen + ATT_BK - 1) / ATT_BK);
+      if (p.causal) nblk = min(nblk, (q_hi - 1) / ATT_BK + 1);
+    }
+  }
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -84,8 +100,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&s_empty[i], ATT_SOFTMAX_THREADS);
+      mbar_init(&p_full[i], ATT_SOFTMAX_THREADS);
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_full, 1);
@@ -170,17 +186,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else {
     // ===================== softmax / epilogue warps =====================
-    const int quad = warp & 3;
+    const int quad = warp & 3;                   // TMEM lane quadrant (hardware rule: warp_id % 4)
+    const int half = (warp - 2) >> 2;            // which 64-key panel of each 128-key block this warp owns
     const int r = quad * 32 + lane;
     const int q = q0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const int qlen = __ldg(p.q_len + b);
-    const int klen = __ldg(p.k_len + b);
     const bool row_dead = (q >= qlen) || (klen <= 0);      // fully masked row -> uniform over Tk
     const bool row_store = q < p.Tq;
     const float sl2 = p.scale * 1.4426950408889634f;       // scale * log2(e)
     const float inv_tk = 1.0f / static_cast<float>(p.Tk);
     uint32_t v[32];
+    auto softmax_bar = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
 
     // ---- pass 1: row maximum (and denominator if the alignments are written)
     float m = -INFINITY;
@@ -189,40 +205,57 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int st = i & 1;
       mbar_wait(&s_full[st], (i >> 1) & 1);
       tc_fence_after();
-      float bm = -INFINITY;
-      for (int c = 0; c < ATT_BK / 32; ++c) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         __syncwarp();
-        tmem_ld32(tmem_S + st * ATT_BK + lane_off + c * 32, v);
+        tmem_ld32(tmem_S + st * ATT_BK + lane_off + half * 64 + c * 32, v);
         tmem_wait_ld();
-        const int kk0 = i * ATT_BK + c * 32;
+        const int kk0 = i * ATT_BK + half * 64 + c * 32;
+        float bm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const int kk = kk0 + e;
           const bool ok = (kk < klen) && (!p.causal || kk <= q);
-          const float s = ok ? __uint_as_float(v[e]) : -INFINITY;
-          bm = fmaxf(bm, s);
-          if (kWriteAli) v[e] = __float_as_uint(s);
+          const float sv = ok ? __uint_as_float(v[e]) : -INFINITY;
+          bm[e & 3] = fmaxf(bm[e & 3], sv);
+          if (kWriteAli) v[e] = __float_as_uint(sv);
         }
-        if (kWriteAli && !row_dead) {
-          const float mn = fmaxf(m, bm);
+        const float cm = fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3]));
+        if (kWriteAli) {
+          const float mn = fmaxf(m, cm);
           if (mn > -INFINITY) {
-            float add = 0.f;
+            float add[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int e = 0; e < 32; ++e) add += exp2f((__uint_as_float(v[e]) - mn) * sl2);
-            l = l * exp2f((m - mn) * sl2) + add;
+            for (int e = 0; e < 32; ++e) add[e & 3] += ex2_approx((__uint_as_float(v[e]) - mn) * sl2);
+            l = l * ex2_approx((m - mn) * sl2) + (add[0] + add[1]) + (add[2] + add[3]);
             m = mn;
           }
+        } else {
+          m = fmaxf(m, cm);
         }
       }
-      if (!kWriteAli) m = fmaxf(m, bm);
       tc_fence_before();
       mbar_arrive(&s_empty[st]);
+    }
+    // combine the two column halves of every row
+    red[half * ATT_BQ + r] = m;
+    if (kWriteAli) red[2 * ATT_BQ + half * ATT_BQ + r] = l;
+    softmax_bar();
+    {
+      const float mo = red[(half ^ 1) * ATT_BQ + r];
+      const float mn = fmaxf(m, mo);
+      if (kWriteAli) {
+        const float lo = red[2 * ATT_BQ + (half ^ 1) * ATT_BQ + r];
+        l = (mn > -INFINITY) ? l * ex2_approx((m - mn) * sl2) + lo * ex2_approx((mo - mn) * sl2) : 0.f;
+      }
+      m = mn;
     }
     if (row_dead) { m = 0.f; l = 1.f; }
 
     // ---- pass 2: probabilities -> shared memory (A operand of P V), denominators, alignments
-    float lsum = 0.f;
+    float ls[4] = {0.f, 0.f, 0.f, 0.f};
     const float inv_l = kWriteAli ? 1.0f / l : 1.0f;
+    const float msl2 = m * sl2;
     for (int iv = 0; iv < nblk; ++iv) {
       const int i = nblk + iv;
       const int st = i & 1;
@@ -230,12 +263,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(&s_full[st], (i >> 1) & 1);
       mbar_wait(&p_empty[sp], ((iv >> 1) & 1) ^ 1);
       tc_fence_after();
-      uint8_t* prow = sP + sp * ATT_PBYTES + r * 128;
-      for (int c = 0; c < ATT_BK / 32; ++c) {
+      // this warp's 64-key panel of the P tile: 128 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7)
+      uint8_t* prow = sP + sp * ATT_PBYTES + half * (ATT_PBYTES / 2) + r * 128;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         __syncwarp();
-        tmem_ld32(tmem_S + st * ATT_BK + lane_off + c * 32, v);
+        tmem_ld32(tmem_S + st * ATT_BK + lane_off + half * 64 + c * 32, v);
         tmem_wait_ld();
-        const int kk0 = iv * ATT_BK + c * 32;
+        const int kk0 = iv * ATT_BK + half * 64 + c * 32;
         float pr[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
@@ -245,22 +280,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             pe = (kk < p.Tk) ? inv_tk : 0.f;
           } else {
             const bool ok = (kk < klen) && (!p.causal || kk <= q);
-            pe = ok ? exp2f((__uint_as_float(v[e]) - m) * sl2) : 0.f;
+            pe = ok ? ex2_approx(__uint_as_float(v[e]) * sl2 - msl2) : 0.f;
           }
-          lsum += pe;
+          ls[e & 3] += pe;
           pr[e] = pe * inv_l;           // normalised already when kWriteAli (inv_l == 1 otherwise)
         }
-        // 4 x 16-byte chunks into the 128B-swizzled K-major layout: panel = 64 keys, chunk ^= (row & 7)
-        uint8_t* panel = prow + (c >> 1) * (ATT_PBYTES / 2);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const int chunk = (c & 1) * 4 + g;
+          const int chunk = c * 4 + g;
           uint4 u;
           u.x = pack_half2(pr[g * 8 + 0], pr[g * 8 + 1]);
           u.y = pack_half2(pr[g * 8 + 2], pr[g * 8 + 3]);
           u.z = pack_half2(pr[g * 8 + 4], pr[g * 8 + 5]);
           u.w = pack_half2(pr[g * 8 + 6], pr[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(panel + ((chunk ^ (r & 7)) << 4)) = u;
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = u;
         }
         if (kWriteAli && row_store) {
           float* arow = p.ali + ((static_cast<long>(b) * p.H + h) * p.Tq + q) * p.Tk + kk0;
@@ -272,26 +305,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_arrive(&p_full[sp]);
       mbar_arrive(&s_empty[st]);
     }
+    // alignments of skipped key blocks are exact zeros (they only exist when the tile has no dead rows)
+    if (kWriteAli && row_store) {
+      const int k_done = nblk * ATT_BK;
+      float* arow = p.ali + ((static_cast<long>(b) * p.H + h) * p.Tq + q) * p.Tk;
+      for (int kk = k_done + half; kk < p.Tk; kk += 2) arow[kk] = 0.f;
+    }
 
-    // ---- epilogue: ctx = O / l
+    // ---- epilogue: ctx = O / l ; each half handles 32 of the 64 head channels
+    float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+    red[4 * ATT_BQ + half * ATT_BQ + r] = lsum;
+    softmax_bar();
+    lsum += red[4 * ATT_BQ + (half ^ 1) * ATT_BQ + r];
     mbar_wait(o_full, 0);
     tc_fence_after();
     const float on = kWriteAli ? 1.0f : 1.0f / lsum;
-    for (int c = 0; c < ATT_D / 32; ++c) {
-      __syncwarp();
-      tmem_ld32(tmem_O + lane_off + c * 32, v);
-      tmem_wait_ld();
-      if (row_store) {
-        __half* dst = p.ctx + (static_cast<long>(b) * p.Tq + q) * p.ctx_ld + h * ATT_D + c * 32;
+    __syncwarp();
+    tmem_ld32(tmem_O + lane_off + half * 32, v);
+    tmem_wait_ld();
+    if (row_store) {
+      __half* dst = p.ctx + (static_cast<long>(b) * p.Tq + q) * p.ctx_ld + h * ATT_D + half * 32;
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 u;
-          u.x = pack_half2(__uint_as_float(v[j]) * on, __uint_as_float(v[j + 1]) * on);
-          u.y = pack_half2(__uint_as_float(v[j + 2]) * on, __uint_as_float(v[j + 3]) * on);
-          u.z = pack_half2(__uint_as_float(v[j + 4]) * on, __uint_as_float(v[j + 5]) * on);
-          u.w = pack_half2(__uint_as_float(v[j + 6]) * on, __uint_as_float(v[j + 7]) * on);
-          *reinterpret_cast<uint4*>(dst + j) = u;
-        }
+      for (int j = 0; j < 32; j += 8) {
+        uint4 u;
+        u.x = pack_half2(__uint_as_float(v[j]) * on, __uint_as_float(v[j + 1]) * on);
+        u.y = pack_half2(__uint_as_float(v[j + 2]) * on, __uint_as_float(v[j + 3]) * on);
+        u.z = pack_half2(__uint_as_float(v[j + 4]) * on, __uint_as_float(v[j + 5]) * on);
+        u.w = pack_half2(__uint_as_float(v[j + 6]) * on, __uint_as_float(v[j + 7]) * on);
+        *reinterpret_cast<uint4*>(dst + j) = u;
       }
     }
     tc_fence_before();

@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // stays in the shared address space (LDS/STS, not generic)
+  if ((smem_u32(smem) & 1023u) != 0) __trap();        // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -189,127 +189,165 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // TMEM gives thread == row.  To keep every global access coalesced the accumulator chunk is
+    // transposed through shared memory (the pipeline stages are idle once tmem_full has fired):
+    // T[row][col] with row stride 65 floats, then lane == column pair and the warp walks the 32 rows.
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
-    const int r = quad * 32 + lane;                  // row inside the tile
+    const int r = quad * 32 + lane;                  // row inside the tile (thread == row view)
     const int t_in_batch = tile_t0 + r;
     const bool row_ok = t_in_batch < p.rows;
     const long grow = static_cast<long>(tile_b) * p.rows + t_in_batch;   // flattened row
     const int sb = static_cast<int>(grow / p.seq_T);
     const int st = static_cast<int>(grow % p.seq_T);
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const long grow0 = static_cast<long>(tile_b) * p.rows + tile_t0 + quad * 32;   // first row of this warp
+    const int rows_here = min(32, p.rows - (tile_t0 + quad * 32));                  // valid rows of this warp (may be <= 0)
+    constexpr int TS = 65;
+    float* T = reinterpret_cast<float*>(smem_a) + (warp - 2) * (32 * TS);
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    uint32_t v[32];
+    uint32_t v[32], w[32];
 
     if (p.mode == EPI_PLAIN || p.mode == EPI_QKV) {
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int n0 = n_tile * BLOCK_N + c * 32;
+      for (int dc = 0; dc < BLOCK_N / 64; ++dc) {
+        const int n0 = n_tile * BLOCK_N + dc * 64;
         if (n0 >= p.N) break;
         __syncwarp();
-        tmem_ld32(taddr + c * 32, v);
+        tmem_ld32(taddr + dc * 64, v);
+        tmem_ld32(taddr + dc * 64 + 32, w);
         tmem_wait_ld();
-        if (!row_ok) continue;   // predicated stores only; the warp re-converges at __syncwarp()
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + j;
-          float x = __uint_as_float(v[j]);
-          if (n < p.N) {
-            if (p.bias) x += __ldg(p.bias + n);
-            x = apply_act(x, p.act);
-            if (p.ch_scale) x = x * __ldg(p.ch_scale + n) + __ldg(p.ch_shift + n);
-            if (p.add_table) x += __ldg(p.add_scale) * __ldg(p.add_table + static_cast<long>(st) * p.add_ld + n);
-            if (p.residual) x += __ldg(p.residual + grow * p.res_ld + n);
-          }
-          f[j] = x;
-        }
         if (p.mode == EPI_QKV && n0 >= p.n_rowmajor) {
-          // V^T store: [blk][b][h][64][vt_ld]; consecutive lanes = consecutive t -> coalesced
-          const int nv = n0 - p.n_rowmajor;
-          const int hd = p.heads * 64;
-          const int blk = nv / hd;
-          const int h = (nv % hd) / 64;
-          const int d0 = nv % 64;
-          __half* dst = p.vt + ((static_cast<long>(blk) * p.seq_B + sb) * p.heads + h) * 64 * p.vt_ld + st;
+          // V^T store: [blk][b][h][64][vt_ld]; thread == row == consecutive t -> already coalesced
+          if (row_ok) {
+            const int nv = n0 - p.n_rowmajor;
+            const int hd = p.heads * 64;
+            const int blk = nv / hd;
+            const int h = (nv % hd) / 64;
+            __half* dst = p.vt + ((static_cast<long>(blk) * p.seq_B + sb) * p.heads + h) * 64 * p.vt_ld + st;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dst[static_cast<long>(d0 + j) * p.vt_ld] = __float2half_rn(f[j]);
+            for (int j = 0; j < 32; ++j) {
+              dst[static_cast<long>(j) * p.vt_ld] = __float2half_rn(__uint_as_float(v[j]));
+              dst[static_cast<long>(32 + j) * p.vt_ld] = __float2half_rn(__uint_as_float(w[j]));
+            }
+          }
           continue;
         }
-        const bool full = (n0 + 32 <= p.N);
-        if (p.out_f32) {
-          float* dst = p.out_f32 + grow * p.ld_f32 + n0;
-          if (full && (p.ld_f32 & 3) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            for (int j = 0; j < 32 && n0 + j < p.N; ++j) dst[j] = f[j];
-          }
+        for (int j = 0; j < 32; ++j) {
+          T[lane * TS + j] = __uint_as_float(v[j]);
+          T[lane * TS + 32 + j] = __uint_as_float(w[j]);
         }
-        if (p.out_h) {
-          __half* dst = p.out_h + grow * p.ld_h + n0;
-          __half* dlo = p.out_lo ? p.out_lo + grow * p.ld_h + n0 : nullptr;
-          if (full && (p.ld_h & 7) == 0) {
+        __syncwarp();
+        const int c0 = n0 + 2 * lane;
+        const bool ok0 = c0 < p.N, ok1 = c0 + 1 < p.N;
+        float b0 = 0.f, b1 = 0.f, s0 = 1.f, s1 = 1.f, h0 = 0.f, h1 = 0.f;
+        if (p.bias) { if (ok0) b0 = __ldg(p.bias + c0); if (ok1) b1 = __ldg(p.bias + c0 + 1); }
+        if (p.ch_scale) {
+          if (ok0) { s0 = __ldg(p.ch_scale + c0); h0 = __ldg(p.ch_shift + c0); }
+          if (ok1) { s1 = __ldg(p.ch_scale + c0 + 1); h1 = __ldg(p.ch_shift + c0 + 1); }
+        }
+        const float tscale = p.add_table ? __ldg(p.add_scale) : 0.f;
+        for (int i0 = 0; i0 < rows_here; i0 += 8) {
+          // issue the row-dependent global loads of 8 rows first (memory-level parallelism), then compute
+          float2 rq[8], tq[8];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u;
-              u.x = pack_half2(f[j], f[j + 1]);
-              u.y = pack_half2(f[j + 2], f[j + 3]);
-              u.z = pack_half2(f[j + 4], f[j + 5]);
-              u.w = pack_half2(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(dst + j) = u;
-            }
-            if (dlo) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                float g[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) g[e] = f[j + e] - __half2float(__float2half_rn(f[j + e]));
-                uint4 u;
-                u.x = pack_half2(g[0], g[1]);
-                u.y = pack_half2(g[2], g[3]);
-                u.z = pack_half2(g[4], g[5]);
-                u.w = pack_half2(g[6], g[7]);
-                *reinterpret_cast<uint4*>(dlo + j) = u;
+          for (int u = 0; u < 8; ++u) {
+            rq[u] = make_float2(0.f, 0.f);
+            tq[u] = make_float2(0.f, 0.f);
+            const int i = i0 + u;
+            if (i < rows_here) {
+              if (p.residual) {
+                const float* rr = p.residual + (grow0 + i) * p.res_ld + c0;
+                if (ok1) rq[u] = *reinterpret_cast<const float2*>(rr);
+                else if (ok0) rq[u].x = rr[0];
+              }
+              if (p.add_table) {
+                const int sti = __shfl_sync(0xffffffffu, st, i);
+                const float* tr = p.add_table + static_cast<long>(sti) * p.add_ld + c0;
+                if (ok1) tq[u] = *reinterpret_cast<const float2*>(tr);
+                else if (ok0) tq[u].x = tr[0];
               }
             }
-          } else {
-            for (int j = 0; j < 32 && n0 + j < p.N; ++j) {
-              const __half hi = __float2half_rn(f[j]);
-              dst[j] = hi;
-              if (dlo) dlo[j] = __float2half_rn(f[j] - __half2float(hi));
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u;
+            if (i >= rows_here) break;
+            const long gr = grow0 + i;
+            float x0 = apply_act(T[i * TS + 2 * lane] + b0, p.act);
+            float x1 = apply_act(T[i * TS + 2 * lane + 1] + b1, p.act);
+            if (p.ch_scale) { x0 = x0 * s0 + h0; x1 = x1 * s1 + h1; }
+            x0 += tscale * tq[u].x + rq[u].x;
+            x1 += tscale * tq[u].y + rq[u].y;
+            if (p.out_f32) {
+              float* dst = p.out_f32 + gr * p.ld_f32 + c0;
+              if (ok1) *reinterpret_cast<float2*>(dst) = make_float2(x0, x1);
+              else if (ok0) dst[0] = x0;
+            }
+            if (p.out_h) {
+              const __half2 hh = __floats2half2_rn(x0, x1);
+              __half* dst = p.out_h + gr * p.ld_h + c0;
+              if (ok1) *reinterpret_cast<__half2*>(dst) = hh;
+              else if (ok0) dst[0] = __low2half(hh);
+              if (p.out_lo) {
+                const float2 hf = __half22float2(hh);
+                const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                __half* dlo = p.out_lo + gr * p.ld_h + c0;
+                if (ok1) *reinterpret_cast<__half2*>(dlo) = ll;
+                else if (ok0) dlo[0] = __low2half(ll);
+              }
             }
           }
         }
       }
     } else if (p.mode == EPI_LN) {
-      // pass 1: x = acc + bias + residual ; row sum ; x written back to TMEM
+      // pass A: x = acc + bias + residual (coalesced), row sums, x written back to TMEM
       float sum = 0.f;
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int dc = 0; dc < BLOCK_N / 64; ++dc) {
         __syncwarp();
-        tmem_ld32(taddr + c * 32, v);
+        tmem_ld32(taddr + dc * 64, v);
+        tmem_ld32(taddr + dc * 64 + 32, w);
         tmem_wait_ld();
-        const int n0 = c * 32;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row_ok && p.residual) rs = *reinterpret_cast<const float4*>(p.residual + grow * p.res_ld + n0 + j);
-          const float rr[4] = {rs.x, rs.y, rs.z, rs.w};
+        for (int j = 0; j < 32; ++j) {
+          T[lane * TS + j] = __uint_as_float(v[j]);
+          T[lane * TS + 32 + j] = __uint_as_float(w[j]);
+        }
+        __syncwarp();
+        const int c0 = dc * 64 + 2 * lane;
+        const float b0 = p.bias ? __ldg(p.bias + c0) : 0.f, b1 = p.bias ? __ldg(p.bias + c0 + 1) : 0.f;
+        for (int i0 = 0; i0 < rows_here; i0 += 16) {
+          float2 q[16];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = __uint_as_float(v[j + e]) + rr[e];
-            if (p.bias) x += __ldg(p.bias + n0 + j + e);
-            sum += x;
-            v[j + e] = __float_as_uint(x);
+          for (int u = 0; u < 16; ++u) {
+            q[u] = make_float2(0.f, 0.f);
+            if (p.residual && i0 + u < rows_here)
+              q[u] = *reinterpret_cast<const float2*>(p.residual + (grow0 + i0 + u) * p.res_ld + c0);
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int i = i0 + u;
+            if (i < rows_here) {
+              T[i * TS + 2 * lane] += b0 + q[u].x;
+              T[i * TS + 2 * lane + 1] += b1 + q[u].y;
+            }
           }
         }
         __syncwarp();
-        tmem_st32(taddr + c * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float a = T[lane * TS + j], b = T[lane * TS + 32 + j];
+          sum += a + b;
+          v[j] = __float_as_uint(a);
+          w[j] = __float_as_uint(b);
+        }
+        tmem_st32(taddr + dc * 64, v);
+        tmem_st32(taddr + dc * 64 + 32, w);
       }
       tmem_wait_st();
       const float mean = sum * (1.f / BLOCK_N);
-      // pass 2: centred second moment
+      // pass B: centred second moment (TMEM reads only)
       float sq = 0.f;
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         __syncwarp();
@@ -322,60 +360,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
       const float rstd = 1.f / sqrtf(sq * (1.f / BLOCK_N) + p.ln_eps);
-      // pass 3: normalise + store
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      // pass C: normalise (thread == row), transpose, gamma/beta + coalesced stores (lane == column pair)
+      for (int dc = 0; dc < BLOCK_N / 64; ++dc) {
         __syncwarp();
-        tmem_ld32(taddr + c * 32, v);
+        tmem_ld32(taddr + dc * 64, v);
+        tmem_ld32(taddr + dc * 64 + 32, w);
         tmem_wait_ld();
-        if (!row_ok) continue;
-        const int n0 = c * 32;
-        float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          f[j] = (__uint_as_float(v[j]) - mean) * rstd * __ldg(p.ln_gamma + n0 + j) + __ldg(p.ln_beta + n0 + j);
-        if (p.out_f32) {
-          float* dst = p.out_f32 + grow * p.ld_f32 + n0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        for (int j = 0; j < 32; ++j) {
+          T[lane * TS + j] = (__uint_as_float(v[j]) - mean) * rstd;
+          T[lane * TS + 32 + j] = (__uint_as_float(w[j]) - mean) * rstd;
         }
-        if (p.out_h) {
-          __half* dst = p.out_h + grow * p.ld_h + n0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 u;
-            u.x = pack_half2(f[j], f[j + 1]);
-            u.y = pack_half2(f[j + 2], f[j + 3]);
-            u.z = pack_half2(f[j + 4], f[j + 5]);
-            u.w = pack_half2(f[j + 6], f[j + 7]);
-            *reinterpret_cast<uint4*>(dst + j) = u;
-          }
+        __syncwarp();
+        const int c0 = dc * 64 + 2 * lane;
+        const float g0 = __ldg(p.ln_gamma + c0), g1 = __ldg(p.ln_gamma + c0 + 1);
+        const float e0 = __ldg(p.ln_beta + c0), e1 = __ldg(p.ln_beta + c0 + 1);
+        for (int i = 0; i < rows_here; ++i) {
+          const long gr = grow0 + i;
+          const float y0 = T[i * TS + 2 * lane] * g0 + e0;
+          const float y1 = T[i * TS + 2 * lane + 1] * g1 + e1;
+          if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + gr * p.ld_f32 + c0) = make_float2(y0, y1);
+          if (p.out_h) *reinterpret_cast<__half2*>(p.out_h + gr * p.ld_h + c0) = __floats2half2_rn(y0, y1);
         }
       }
     } else if (p.mode == EPI_COUPLING) {
-      // columns [0, half) = log_scale, [half, 2*half) = shift, half = N / 2 (modules/flow.py:223-257)
+      // columns [0, half) = log_scale, [half, 2*half) = shift, half = N / 2 (modules/flow.py:223-257).
+      // Per 32 latent channels: T[row][0..31] = log_scale, T[row][32..63] = shift; lane == channel.
       const int half = p.N >> 1;
-      const bool in_len = row_ok && (st < __ldg(p.lengths + sb));
+      const int len_b = __ldg(p.lengths + min(sb, p.seq_B - 1));
+      const bool in_len = row_ok && (st < len_b);
       float logdet = 0.f;
-      uint32_t w[32];
       for (int c = 0; c < half / 32; ++c) {
         __syncwarp();
         tmem_ld32(taddr + c * 32, v);
         tmem_ld32(taddr + half + c * 32, w);
         tmem_wait_ld();
-        if (!row_ok) continue;
-        float* zrow = p.z + grow * p.z_ld + p.zp_off + c * 32;
-        __half* zh = p.z_h + grow * p.z_ld + p.zp_off + c * 32;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float ls = __uint_as_float(v[j]) + __ldg(p.bias + c * 32 + j);
-          const float sh = __uint_as_float(w[j]) + __ldg(p.bias + half + c * 32 + j);
+          T[lane * TS + j] = __uint_as_float(v[j]);
+          T[lane * TS + 32 + j] = __uint_as_float(w[j]);
+        }
+        __syncwarp();
+        const int ch = c * 32 + lane;
+        const float bl = __ldg(p.bias + ch), bs = __ldg(p.bias + half + ch);
+        for (int i = 0; i < rows_here; ++i) {
+          const long gr = grow0 + i;
+          const float ls = T[i * TS + lane] + bl;
+          const float sh = T[i * TS + 32 + lane] + bs;
           const float scale = 1.f / (1.f + expf(-(ls + 2.0f)));
-          const float zp = zrow[j];
-          const float o = p.backward ? (zp - sh) / (scale + 1e-12f) : scale * zp + sh;
-          zrow[j] = o;
-          zh[j] = __float2half_rn(o);
-          logdet += logf(scale);
+          float* zp = p.z + gr * p.z_ld + p.zp_off + ch;
+          const float o = p.backward ? (*zp - sh) / (scale + 1e-12f) : scale * (*zp) + sh;
+          *zp = o;
+          p.z_h[gr * p.z_ld + p.zp_off + ch] = __float2half_rn(o);
+          T[i * TS + lane] = logf(scale);
+        }
+        __syncwarp();
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) logdet += T[lane * TS + j];
         }
       }
       if (row_ok) p.row_acc[grow] += in_len ? (p.backward ? -logdet : logdet) : 0.f;
@@ -383,27 +425,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // modules/posterior.py:20-72 with the models.py:136 name swap already applied by the packing order:
       // columns [0, L) = log-variance (mu_projection), [L, 2L) = mean (logvar_projection), L = N / 2.
       const int L = p.N >> 1;
-      const bool in_len = row_ok && (st < __ldg(p.lengths + sb));
+      const int len_b = __ldg(p.lengths + min(sb, p.seq_B - 1));
+      const bool in_len = row_ok && (st < len_b);
       float acc = 0.f;
-      uint32_t w[32];
       for (int c = 0; c < L / 32; ++c) {
         __syncwarp();
         tmem_ld32(taddr + c * 32, v);
         tmem_ld32(taddr + L + c * 32, w);
         tmem_wait_ld();
-        if (!row_ok) continue;
-        const float* er = p.eps_in + grow * p.z_ld + c * 32;
-        float* zrow = p.z + grow * p.z_ld + c * 32;
-        __half* zh = p.z_h + grow * p.z_ld + c * 32;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float lv = __uint_as_float(v[j]) + __ldg(p.bias + c * 32 + j);
-          const float mu = __uint_as_float(w[j]) + __ldg(p.bias + L + c * 32 + j);
-          const float e = er[j];
+          T[lane * TS + j] = __uint_as_float(v[j]);
+          T[lane * TS + 32 + j] = __uint_as_float(w[j]);
+        }
+        __syncwarp();
+        const int ch = c * 32 + lane;
+        const float bl = __ldg(p.bias + ch), bm = __ldg(p.bias + L + ch);
+        for (int i = 0; i < rows_here; ++i) {
+          const long gr = grow0 + i;
+          const float lv = T[i * TS + lane] + bl;
+          const float mu = T[i * TS + 32 + lane] + bm;
+          const float e = __ldg(p.eps_in + gr * p.z_ld + ch);
           const float o = e * expf(0.5f * lv) + mu;
-          zrow[j] = o;
-          zh[j] = __float2half_rn(o);
-          acc += lv + e * e;
+          p.z[gr * p.z_ld + ch] = o;
+          p.z_h[gr * p.z_ld + ch] = __float2half_rn(o);
+          T[i * TS + lane] = lv + e * e;
+        }
+        __syncwarp();
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += T[lane * TS + j];
         }
       }
       if (row_ok) p.row_acc[grow] += in_len ? -0.5f * (static_cast<float>(L) * 1.8378770664093453f + acc) : 0.f;
