@@ -209,11 +209,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tc_fence_after();
     uint32_t v[32], w[32];
 
+    // Warp-private staging slabs (the pipeline stages are idle now): 32 rows x 128 B, 16-byte chunks
+    // XOR-swizzled by (row & 7) so that both the thread==row writes and the cooperative copies are
+    // bank-conflict free.  [res0][res1][f32 0][f32 1][f16][f16-lo], 4 KB each.
+    uint8_t* slab = smem_a + (warp - 2) * (6 * 4096);
+    uint8_t* s_res = slab;
+    uint8_t* s_f32 = slab + 2 * 4096;
+    uint8_t* s_h = slab + 4 * 4096;
+    uint8_t* s_lo = slab + 5 * 4096;
+    auto sw = [&](uint8_t* base, int row, int chunk) -> uint4* {
+      return reinterpret_cast<uint4*>(base + row * 128 + ((chunk ^ (row & 7)) << 4));
+    };
+    // cooperative, coalesced copy of a [rows_here x 32] fp32 global tile <-> slab (4 rows x 128 B per instruction)
+    auto load_f32_slab = [&](uint8_t* base, const float* g, int ld, int col0, int ncols_valid) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + (lane >> 3), chunk = lane & 7;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (row < rows_here && chunk * 4 < ncols_valid)
+          u = __ldg(reinterpret_cast<const uint4*>(g + (grow0 + row) * ld + col0 + chunk * 4));
+        *sw(base, row, chunk) = u;
+      }
+    };
+    auto store_f32_slab = [&](uint8_t* base, float* g, int ld, int col0, int ncols_valid) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + (lane >> 3), chunk = lane & 7;
+        if (row < rows_here && chunk * 4 < ncols_valid)
+          *reinterpret_cast<uint4*>(g + (grow0 + row) * ld + col0 + chunk * 4) = *sw(base, row, chunk);
+      }
+    };
+    auto store_f16_slab = [&](uint8_t* base, __half* g, int ld, int col0, int ncols_valid) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + (lane >> 3), chunk = lane & 7;
+        if (row < rows_here && chunk * 8 < ncols_valid)
+          *reinterpret_cast<uint4*>(g + (grow0 + row) * ld + col0 + chunk * 8) = *sw(base, row, chunk);
+      }
+    };
+
     if (p.mode == EPI_PLAIN || p.mode == EPI_QKV) {
       for (int dc = 0; dc < BLOCK_N / 64; ++dc) {
         const int n0 = n_tile * BLOCK_N + dc * 64;
         if (n0 >= p.N) break;
+        const int nvalid = min(64, p.N - n0);
         __syncwarp();
+        if (p.residual) {
+          load_f32_slab(s_res, p.residual, p.res_ld, n0, nvalid);
+          load_f32_slab(s_res + 4096, p.residual, p.res_ld, n0 + 32, nvalid - 32);
+        }
         tmem_ld32(taddr + dc * 64, v);
         tmem_ld32(taddr + dc * 64 + 32, w);
         tmem_wait_ld();
@@ -233,122 +277,121 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           continue;
         }
+        __syncwarp();   // residual slab visible
+        const float tscale = p.add_table ? __ldg(p.add_scale) : 0.f;
+        const float* trow = p.add_table ? p.add_table + static_cast<long>(st) * p.add_ld + n0 : nullptr;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          T[lane * TS + j] = __uint_as_float(v[j]);
-          T[lane * TS + 32 + j] = __uint_as_float(w[j]);
+        for (int hh = 0; hh < 2; ++hh) {          // the two 32-column halves of this 64-column chunk
+          uint32_t* acc = hh ? w : v;
+          const int nb = n0 + hh * 32;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {           // 4 columns per step
+            float x[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(acc[g * 4 + e]);
+            if (nb + g * 4 < p.N) {
+              if (p.bias) {
+                const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + nb + g * 4));
+                x[0] += bq.x; x[1] += bq.y; x[2] += bq.z; x[3] += bq.w;
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] = apply_act(x[e], p.act);
+              if (p.ch_scale) {
+                const float4 sq = __ldg(reinterpret_cast<const float4*>(p.ch_scale + nb + g * 4));
+                const float4 hq = __ldg(reinterpret_cast<const float4*>(p.ch_shift + nb + g * 4));
+                x[0] = x[0] * sq.x + hq.x; x[1] = x[1] * sq.y + hq.y; x[2] = x[2] * sq.z + hq.z; x[3] = x[3] * sq.w + hq.w;
+              }
+              if (p.add_table && row_ok) {
+                const float4 tq = __ldg(reinterpret_cast<const float4*>(trow + hh * 32 + g * 4));
+                x[0] += tscale * tq.x; x[1] += tscale * tq.y; x[2] += tscale * tq.z; x[3] += tscale * tq.w;
+              }
+              if (p.residual) {
+                const uint4 rq = *sw(s_res + hh * 4096, lane, g);
+                x[0] += __uint_as_float(rq.x); x[1] += __uint_as_float(rq.y);
+                x[2] += __uint_as_float(rq.z); x[3] += __uint_as_float(rq.w);
+              }
+            }
+            if (p.out_f32)
+              *sw(s_f32 + hh * 4096, lane, g) = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]),
+                                                            __float_as_uint(x[2]), __float_as_uint(x[3]));
+            acc[g * 4 + 0] = __float_as_uint(x[0]); acc[g * 4 + 1] = __float_as_uint(x[1]);
+            acc[g * 4 + 2] = __float_as_uint(x[2]); acc[g * 4 + 3] = __float_as_uint(x[3]);
+          }
+          if (p.out_h) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {         // 8 columns -> one 16-byte fp16 chunk
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(acc[g * 8 + e]);
+              uint4 u;
+              u.x = pack_half2(f[0], f[1]); u.y = pack_half2(f[2], f[3]);
+              u.z = pack_half2(f[4], f[5]); u.w = pack_half2(f[6], f[7]);
+              *sw(s_h, lane, hh * 4 + g) = u;
+              if (p.out_lo) {
+                float d[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d[e] = f[e] - __half2float(__float2half_rn(f[e]));
+                uint4 q;
+                q.x = pack_half2(d[0], d[1]); q.y = pack_half2(d[2], d[3]);
+                q.z = pack_half2(d[4], d[5]); q.w = pack_half2(d[6], d[7]);
+                *sw(s_lo, lane, hh * 4 + g) = q;
+              }
+            }
+          }
         }
         __syncwarp();
-        const int c0 = n0 + 2 * lane;
-        const bool ok0 = c0 < p.N, ok1 = c0 + 1 < p.N;
-        float b0 = 0.f, b1 = 0.f, s0 = 1.f, s1 = 1.f, h0 = 0.f, h1 = 0.f;
-        if (p.bias) { if (ok0) b0 = __ldg(p.bias + c0); if (ok1) b1 = __ldg(p.bias + c0 + 1); }
-        if (p.ch_scale) {
-          if (ok0) { s0 = __ldg(p.ch_scale + c0); h0 = __ldg(p.ch_shift + c0); }
-          if (ok1) { s1 = __ldg(p.ch_scale + c0 + 1); h1 = __ldg(p.ch_shift + c0 + 1); }
+        if (p.out_f32) {
+          store_f32_slab(s_f32, p.out_f32, p.ld_f32, n0, nvalid);
+          store_f32_slab(s_f32 + 4096, p.out_f32, p.ld_f32, n0 + 32, nvalid - 32);
         }
-        const float tscale = p.add_table ? __ldg(p.add_scale) : 0.f;
-        for (int i0 = 0; i0 < rows_here; i0 += 8) {
-          // issue the row-dependent global loads of 8 rows first (memory-level parallelism), then compute
-          float2 rq[8], tq[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            rq[u] = make_float2(0.f, 0.f);
-            tq[u] = make_float2(0.f, 0.f);
-            const int i = i0 + u;
-            if (i < rows_here) {
-              if (p.residual) {
-                const float* rr = p.residual + (grow0 + i) * p.res_ld + c0;
-                if (ok1) rq[u] = *reinterpret_cast<const float2*>(rr);
-                else if (ok0) rq[u].x = rr[0];
-              }
-              if (p.add_table) {
-                const int sti = __shfl_sync(0xffffffffu, st, i);
-                const float* tr = p.add_table + static_cast<long>(sti) * p.add_ld + c0;
-                if (ok1) tq[u] = *reinterpret_cast<const float2*>(tr);
-                else if (ok0) tq[u].x = tr[0];
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int i = i0 + u;
-            if (i >= rows_here) break;
-            const long gr = grow0 + i;
-            float x0 = apply_act(T[i * TS + 2 * lane] + b0, p.act);
-            float x1 = apply_act(T[i * TS + 2 * lane + 1] + b1, p.act);
-            if (p.ch_scale) { x0 = x0 * s0 + h0; x1 = x1 * s1 + h1; }
-            x0 += tscale * tq[u].x + rq[u].x;
-            x1 += tscale * tq[u].y + rq[u].y;
-            if (p.out_f32) {
-              float* dst = p.out_f32 + gr * p.ld_f32 + c0;
-              if (ok1) *reinterpret_cast<float2*>(dst) = make_float2(x0, x1);
-              else if (ok0) dst[0] = x0;
-            }
-            if (p.out_h) {
-              const __half2 hh = __floats2half2_rn(x0, x1);
-              __half* dst = p.out_h + gr * p.ld_h + c0;
-              if (ok1) *reinterpret_cast<__half2*>(dst) = hh;
-              else if (ok0) dst[0] = __low2half(hh);
-              if (p.out_lo) {
-                const float2 hf = __half22float2(hh);
-                const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-                __half* dlo = p.out_lo + gr * p.ld_h + c0;
-                if (ok1) *reinterpret_cast<__half2*>(dlo) = ll;
-                else if (ok0) dlo[0] = __low2half(ll);
-              }
-            }
-          }
+        if (p.out_h) {
+          store_f16_slab(s_h, p.out_h, p.ld_h, n0, nvalid);
+          if (p.out_lo) store_f16_slab(s_lo, p.out_lo, p.ld_h, n0, nvalid);
         }
       }
     } else if (p.mode == EPI_LN) {
-      // pass A: x = acc + bias + residual (coalesced), row sums, x written back to TMEM
+      // pass A: x = acc + bias + residual, row sums, x written back to TMEM
       float sum = 0.f;
       for (int dc = 0; dc < BLOCK_N / 64; ++dc) {
+        const int n0 = dc * 64;
         __syncwarp();
-        tmem_ld32(taddr + dc * 64, v);
-        tmem_ld32(taddr + dc * 64 + 32, w);
+        if (p.residual) {
+          load_f32_slab(s_res, p.residual, p.res_ld, n0, 64);
+          load_f32_slab(s_res + 4096, p.residual, p.res_ld, n0 + 32, 32);
+        }
+        tmem_ld32(taddr + n0, v);
+        tmem_ld32(taddr + n0 + 32, w);
         tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          T[lane * TS + j] = __uint_as_float(v[j]);
-          T[lane * TS + 32 + j] = __uint_as_float(w[j]);
-        }
         __syncwarp();
-        const int c0 = dc * 64 + 2 * lane;
-        const float b0 = p.bias ? __ldg(p.bias + c0) : 0.f, b1 = p.bias ? __ldg(p.bias + c0 + 1) : 0.f;
-        for (int i0 = 0; i0 < rows_here; i0 += 16) {
-          float2 q[16];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            q[u] = make_float2(0.f, 0.f);
-            if (p.residual && i0 + u < rows_here)
-              q[u] = *reinterpret_cast<const float2*>(p.residual + (grow0 + i0 + u) * p.res_ld + c0);
-          }
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t* acc = hh ? w : v;
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const int i = i0 + u;
-            if (i < rows_here) {
-              T[i * TS + 2 * lane] += b0 + q[u].x;
-              T[i * TS + 2 * lane + 1] += b1 + q[u].y;
+          for (int g = 0; g < 8; ++g) {
+            float x[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(acc[g * 4 + e]);
+            if (p.bias) {
+              const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + hh * 32 + g * 4));
+              x[0] += bq.x; x[1] += bq.y; x[2] += bq.z; x[3] += bq.w;
             }
+            if (p.residual) {
+              const uint4 rq = *sw(s_res + hh * 4096, lane, g);
+              x[0] += __uint_as_float(rq.x); x[1] += __uint_as_float(rq.y);
+              x[2] += __uint_as_float(rq.z); x[3] += __uint_as_float(rq.w);
+            }
+            sum += (x[0] + x[1]) + (x[2] + x[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[g * 4 + e] = __float_as_uint(x[e]);
           }
         }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float a = T[lane * TS + j], b = T[lane * TS + 32 + j];
-          sum += a + b;
-          v[j] = __float_as_uint(a);
-          w[j] = __float_as_uint(b);
-        }
-        tmem_st32(taddr + dc * 64, v);
-        tmem_st32(taddr + dc * 64 + 32, w);
+        tmem_st32(taddr + n0, v);
+        tmem_st32(taddr + n0 + 32, w);
       }
       tmem_wait_st();
       const float mean = sum * (1.f / BLOCK_N);
       // pass B: centred second moment (TMEM reads only)
-      float sq = 0.f;
+      float sq4[4] = {0.f, 0.f, 0.f, 0.f};
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         __syncwarp();
         tmem_ld32(taddr + c * 32, v);
@@ -356,32 +399,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float d = __uint_as_float(v[j]) - mean;
-          sq += d * d;
+          sq4[j & 3] = fmaf(d, d, sq4[j & 3]);
         }
       }
-      const float rstd = 1.f / sqrtf(sq * (1.f / BLOCK_N) + p.ln_eps);
-      // pass C: normalise (thread == row), transpose, gamma/beta + coalesced stores (lane == column pair)
+      const float rstd = 1.f / sqrtf(((sq4[0] + sq4[1]) + (sq4[2] + sq4[3])) * (1.f / BLOCK_N) + p.ln_eps);
+      // pass C: normalise, gamma/beta, stage, coalesced copy-out
       for (int dc = 0; dc < BLOCK_N / 64; ++dc) {
+        const int n0 = dc * 64;
         __syncwarp();
-        tmem_ld32(taddr + dc * 64, v);
-        tmem_ld32(taddr + dc * 64 + 32, w);
+        tmem_ld32(taddr + n0, v);
+        tmem_ld32(taddr + n0 + 32, w);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          T[lane * TS + j] = (__uint_as_float(v[j]) - mean) * rstd;
-          T[lane * TS + 32 + j] = (__uint_as_float(w[j]) - mean) * rstd;
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t* acc = hh ? w : v;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 gq = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + n0 + hh * 32 + g * 4));
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(p.ln_beta + n0 + hh * 32 + g * 4));
+            float y[4];
+            y[0] = (__uint_as_float(acc[g * 4 + 0]) - mean) * rstd * gq.x + bq.x;
+            y[1] = (__uint_as_float(acc[g * 4 + 1]) - mean) * rstd * gq.y + bq.y;
+            y[2] = (__uint_as_float(acc[g * 4 + 2]) - mean) * rstd * gq.z + bq.z;
+            y[3] = (__uint_as_float(acc[g * 4 + 3]) - mean) * rstd * gq.w + bq.w;
+            if (p.out_f32)
+              *sw(s_f32 + hh * 4096, lane, g) = make_uint4(__float_as_uint(y[0]), __float_as_uint(y[1]),
+                                                            __float_as_uint(y[2]), __float_as_uint(y[3]));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[g * 4 + e] = __float_as_uint(y[e]);
+          }
+          if (p.out_h) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 u;
+              u.x = pack_half2(__uint_as_float(acc[g * 8 + 0]), __uint_as_float(acc[g * 8 + 1]));
+              u.y = pack_half2(__uint_as_float(acc[g * 8 + 2]), __uint_as_float(acc[g * 8 + 3]));
+              u.z = pack_half2(__uint_as_float(acc[g * 8 + 4]), __uint_as_float(acc[g * 8 + 5]));
+              u.w = pack_half2(__uint_as_float(acc[g * 8 + 6]), __uint_as_float(acc[g * 8 + 7]));
+              *sw(s_h, lane, hh * 4 + g) = u;
+            }
+          }
         }
         __syncwarp();
-        const int c0 = dc * 64 + 2 * lane;
-        const float g0 = __ldg(p.ln_gamma + c0), g1 = __ldg(p.ln_gamma + c0 + 1);
-        const float e0 = __ldg(p.ln_beta + c0), e1 = __ldg(p.ln_beta + c0 + 1);
-        for (int i = 0; i < rows_here; ++i) {
-          const long gr = grow0 + i;
-          const float y0 = T[i * TS + 2 * lane] * g0 + e0;
-          const float y1 = T[i * TS + 2 * lane + 1] * g1 + e1;
-          if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + gr * p.ld_f32 + c0) = make_float2(y0, y1);
-          if (p.out_h) *reinterpret_cast<__half2*>(p.out_h + gr * p.ld_h + c0) = __floats2half2_rn(y0, y1);
+        if (p.out_f32) {
+          store_f32_slab(s_f32, p.out_f32, p.ld_f32, n0, 64);
+          store_f32_slab(s_f32 + 4096, p.out_f32, p.ld_f32, n0 + 32, 32);
         }
+        if (p.out_h) store_f16_slab(s_h, p.out_h, p.ld_h, n0, 64);
       }
     } else if (p.mode == EPI_COUPLING) {
       // columns [0, half) = log_scale, [half, 2*half) = shift, half = N / 2 (modules/flow.py:223-257).
