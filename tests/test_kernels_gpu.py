@@ -33,12 +33,15 @@ def test_dense_plain(M, K, N, block_n):
     assert rel_err(out, ref32) < 3e-3, rel_err(out, ref32)
 
 
+@pytest.mark.parametrize("split_cluster", [False, True])
 @pytest.mark.parametrize("M,K,N", [(300, 512, 256), (200, 1024, 256), (148, 768, 512), (131, 1024, 512)])
-def test_dense_layernorm(M, K, N):
+def test_dense_layernorm(M, K, N, split_cluster):
+    """GEMM + bias + residual + LayerNorm epilogue; split_cluster: N split over a 2-CTA cluster with the
+    row statistics exchanged through distributed shared memory."""
     import gpu_util as G
     A, W, b = gen(M, K, seed=4), gen(K, N, seed=5, scale=1 / math.sqrt(K)), gen(N, seed=6)
     res, gamma, beta = gen(M, N, seed=7), 1 + 0.1 * gen(N, seed=8), 0.1 * gen(N, seed=9)
-    out = G.dense(A, W, b, residual=res, gamma=gamma, beta=beta, ln=True, block_n=N)
+    out = G.dense(A, W, b, residual=res, gamma=gamma, beta=beta, ln=True, block_n=N // 2 if split_cluster else N)
     x = A.half().float() @ W.half().float() + b + res
     mean = x.mean(-1, keepdim=True)
     var = ((x - mean) ** 2).mean(-1, keepdim=True)

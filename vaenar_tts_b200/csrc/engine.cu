@@ -532,7 +532,10 @@ static void run_gemm(Ctx& c, int block_n, AOp a0, AOp a1, int batches, int rows,
   int tk = 0;
   for (int s = 0; s < p.nseg; ++s) tk += p.seg_kblocks[s];
   if (tk * 64 != Ktot) VB_THROW("gemm: segments cover %d of K %d", tk * 64, Ktot);
-  if ((p.mode == EPI_LN || p.mode == EPI_COUPLING || p.mode == EPI_POSTERIOR) && p.N != block_n)
+  // LayerNorm over N = 2 * BLOCK_N: split the columns over a 2-CTA cluster (row statistics via DSMEM)
+  p.ln_cluster = (p.mode == EPI_LN && p.N == 2 * block_n) ? 1 : 0;
+  if ((p.mode == EPI_LN && !p.ln_cluster && p.N != block_n) ||
+      ((p.mode == EPI_COUPLING || p.mode == EPI_POSTERIOR) && p.N != block_n))
     VB_THROW("gemm: row-wise epilogue needs BLOCK_N == N (%d vs %d)", block_n, p.N);
   p.batches = batches;
   p.rows = rows;
@@ -547,12 +550,26 @@ static void run_gemm(Ctx& c, int block_n, AOp a0, AOp a1, int batches, int rows,
   const double kalg = p.alg_k > 0 ? p.alg_k : Ktot;   // algorithmic K: no padding, no split-fp16 triple
   const char* cls = p.mode == EPI_LN ? "gemm_ln" : (p.nseg >= 5 ? "gemm_conv" : (p.mode == EPI_QKV ? "gemm_qkv" : "gemm_plain"));
   ProfileScope prof(cls, 2.0 * Mrows * p.N * kalg, Mrows * kalg * 2 + static_cast<double>(p.N) * Ktot * 2 + Mrows * p.N * 6, c.stream);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.stream = c.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = p.ln_cluster ? 2 : 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le;
   switch (block_n) {
-    case 128: gemm_tc_kernel<128><<<grid, GEMM_THREADS, GemmCfg<128>::kSmemBytes, c.stream>>>(tA0, tA1, tB, p); break;
-    case 256: gemm_tc_kernel<256><<<grid, GEMM_THREADS, GemmCfg<256>::kSmemBytes, c.stream>>>(tA0, tA1, tB, p); break;
-    case 512: gemm_tc_kernel<512><<<grid, GEMM_THREADS, GemmCfg<512>::kSmemBytes, c.stream>>>(tA0, tA1, tB, p); break;
+    case 128: cfg.dynamicSmemBytes = GemmCfg<128>::kSmemBytes; le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<128>, tA0, tA1, tB, p); break;
+    case 256: cfg.dynamicSmemBytes = GemmCfg<256>::kSmemBytes; le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256>, tA0, tA1, tB, p); break;
+    case 512: cfg.dynamicSmemBytes = GemmCfg<512>::kSmemBytes; le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<512>, tA0, tA1, tB, p); break;
     default: VB_THROW("unsupported BLOCK_N %d", block_n);
   }
+  if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(gemm_tc_kernel<%d>) failed: %s", block_n, cudaGetErrorString(le));
   check_launch("gemm_tc_kernel");
 }
 
@@ -675,7 +692,7 @@ static void xblk_fwd(Ctx& c, const std::string& pk, const std::string& pn, Strea
     p.bias = c.P(pn + ".att_proj1.bias"); p.residual = x.f; p.res_ld = d;
     p.ln_gamma = c.P(pn + ".layer_norm1.gamma"); p.ln_beta = c.P(pn + ".layer_norm1.beta");
     p.out_f32 = b.s.f; p.ld_f32 = d; p.out_h = b.s.h; p.ld_h = d;
-    run_gemm(c, d, AOp{x.h, d, d}, AOp{b.ctx, d, d}, 1, rows, c.W(pk + ".proj1"), 2 * d, d, p);
+    run_gemm(c, d / 2, AOp{x.h, d, d}, AOp{b.ctx, d, d}, 1, rows, c.W(pk + ".proj1"), 2 * d, d, p);
   }
   {  // cross-attention query projection
     GemmParams p = gp();
@@ -692,7 +709,7 @@ static void xblk_fwd(Ctx& c, const std::string& pk, const std::string& pn, Strea
     p.bias = c.P(pn + ".att_proj2.bias"); p.residual = b.s.f; p.res_ld = d;
     p.ln_gamma = c.P(pn + ".layer_norm2.gamma"); p.ln_beta = c.P(pn + ".layer_norm2.beta");
     p.out_f32 = b.cst.f; p.ld_f32 = d; p.out_h = b.cst.h; p.ld_h = d;
-    run_gemm(c, d, AOp{b.s.h, d, d}, AOp{b.ctx, d, d}, 1, rows, c.W(pk + ".proj2"), 2 * d, d, p);
+    run_gemm(c, d / 2, AOp{b.s.h, d, d}, AOp{b.ctx, d, d}, 1, rows, c.W(pk + ".proj2"), 2 * d, d, p);
   }
   {  // FFN (modules/utils.py:48-53)
     GemmParams p = gp();
@@ -706,7 +723,7 @@ static void xblk_fwd(Ctx& c, const std::string& pk, const std::string& pn, Strea
     p.bias = c.P(pn + ".ffn.dense2.bias"); p.residual = b.cst.f; p.res_ld = d;
     p.ln_gamma = c.P(pn + ".ffn.layer_norm.gamma"); p.ln_beta = c.P(pn + ".ffn.layer_norm.beta");
     p.out_f32 = x.f; p.ld_f32 = d; p.out_h = x.h; p.ld_h = d;
-    run_gemm(c, d, AOp{b.hid, ffn, ffn}, AOp{}, 1, rows, c.W(pk + ".ffn2"), ffn, d, p);
+    run_gemm(c, d / 2, AOp{b.hid, ffn, ffn}, AOp{}, 1, rows, c.W(pk + ".ffn2"), ffn, d, p);
   }
 }
 
@@ -771,7 +788,7 @@ static void encoder_fwd(Ctx& c, const int* texts, const int* t_len, int B, int T
       p.bias = c.P(pn + ".att_proj.bias"); p.residual = text_embd; p.res_ld = E;
       p.ln_gamma = c.P(pn + ".layer_norm.gamma"); p.ln_beta = c.P(pn + ".layer_norm.beta");
       p.out_f32 = hf; p.ld_f32 = E; p.out_h = hh; p.ld_h = E;
-      run_gemm(c, E, AOp{xa, E, E}, AOp{ctx, A, A}, 1, static_cast<int>(rows), c.W(pk + ".proj"), E + A, E, p);
+      run_gemm(c, E / 2, AOp{xa, E, E}, AOp{ctx, A, A}, 1, static_cast<int>(rows), c.W(pk + ".proj"), E + A, E, p);
     }
     {
       GemmParams p = gp();
@@ -785,7 +802,7 @@ static void encoder_fwd(Ctx& c, const int* texts, const int* t_len, int B, int T
       p.bias = c.P(pn + ".ffn.dense2.bias"); p.residual = hf; p.res_ld = E;
       p.ln_gamma = c.P(pn + ".ffn.layer_norm.gamma"); p.ln_beta = c.P(pn + ".ffn.layer_norm.beta");
       p.out_f32 = text_embd; p.ld_f32 = E; p.out_h = xa; p.ld_h = E;
-      run_gemm(c, E, AOp{hid, F, F}, AOp{}, 1, static_cast<int>(rows), c.W(pk + ".ffn2"), F, E, p);
+      run_gemm(c, E / 2, AOp{hid, F, F}, AOp{}, 1, static_cast<int>(rows), c.W(pk + ".ffn2"), F, E, p);
     }
   }
   c.ws_off = mark;

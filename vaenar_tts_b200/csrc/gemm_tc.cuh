@@ -11,7 +11,8 @@
 //     - split-fp16 ("3x"):      segments (hi, lo, hi) against packed weights [Whi | Whi | Wlo]
 // * W is packed fp16 [N, K_total] (K-major), accumulators are fp32 in TMEM.
 // * One CTA = one 128 x BLOCK_N output tile.  Warp 0: TMA producer, warp 1: MMA issuer (one elected
-//   thread), warps 2..5: epilogue (thread == output row, TMEM lane == row).
+//   thread), warps 2..9: epilogue (thread == output row, TMEM lane == row; two warps per TMEM lane
+//   quadrant, each taking alternate 64-column chunks; LayerNorm row statistics are combined through shared memory).
 #pragma once
 #include "ptx.cuh"
 
@@ -20,7 +21,8 @@ namespace vb {
 constexpr int kMaxSegs = 16;
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int GEMM_EPI_THREADS = 256;
 
 enum EpiMode : int {
   EPI_PLAIN = 0,     // act(acc + bias) [*scale + shift] [+ a * table[t]] [+ residual] -> f32 / f16 / f16-lo
@@ -41,6 +43,7 @@ struct GemmParams {
   int seg_shift[kMaxSegs];
   int seg_kblocks[kMaxSegs];
   int alg_k;             // algorithmic K (host-side accounting only)
+  int ln_cluster;        // EPI_LN: N is split over a 2-CTA cluster (blockIdx.y = rank), stats exchanged via DSMEM
   // ---- sequence geometry of the flattened rows (row = b * seq_T + t)
   int seq_T;
   int seq_B;
@@ -86,7 +89,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BLOCK_N <= 128) ? 6 : (BLOCK_N <= 256 ? 4 : 2);
   static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*cluster LN exchange*/;
   static constexpr int kUmmaN = BLOCK_N > 256 ? 256 : BLOCK_N;
   static constexpr int kNumUmmaN = BLOCK_N / kUmmaN;
 };
@@ -111,6 +114,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 1);
+  uint64_t* xbar = bars + 2 * Cfg::kStages + 2;             // [2] cluster LayerNorm exchange
+  float* xred = reinterpret_cast<float*>(bars + 2 * Cfg::kStages + 4);   // [2][128] written by the peer CTA
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,6 +133,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(&xbar[0], 128);
+    mbar_init(&xbar[1], 128);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -138,6 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (p.ln_cluster) cluster_sync_all();   // peer barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -203,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const long grow0 = static_cast<long>(tile_b) * p.rows + tile_t0 + quad * 32;   // first row of this warp
     const int rows_here = min(32, p.rows - (tile_t0 + quad * 32));                  // valid rows of this warp (may be <= 0)
     constexpr int TS = 65;
-    float* T = reinterpret_cast<float*>(smem_a) + (warp - 2) * (32 * TS);
+    float* T = reinterpret_cast<float*>(smem_a + (warp - 2) * (4 * 4096));   // 8320 B of this warp's 16 KB
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
@@ -211,12 +219,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
     // Warp-private staging slabs (the pipeline stages are idle now): 32 rows x 128 B, 16-byte chunks
     // XOR-swizzled by (row & 7) so that both the thread==row writes and the cooperative copies are
-    // bank-conflict free.  [res0][res1][f32 0][f32 1][f16][f16-lo], 4 KB each.
-    uint8_t* slab = smem_a + (warp - 2) * (6 * 4096);
+    // bank-conflict free.  [res0 | f32 0][res1 | f32 1][f16][f16-lo], 4 KB each: the fp32 output staging
+    // aliases the residual slabs (a thread reads its own residual chunk before overwriting it).
+    const int half = (warp - 2) >> 2;                // which alternate 64-column chunks this warp handles
+    uint8_t* slab = smem_a + (warp - 2) * (4 * 4096);
     uint8_t* s_res = slab;
-    uint8_t* s_f32 = slab + 2 * 4096;
-    uint8_t* s_h = slab + 4 * 4096;
-    uint8_t* s_lo = slab + 5 * 4096;
+    uint8_t* s_f32 = slab;
+    uint8_t* s_h = slab + 2 * 4096;
+    uint8_t* s_lo = slab + 3 * 4096;
+    float* red = reinterpret_cast<float*>(smem_a + 8 * 4 * 4096);   // [2][128] LayerNorm partial exchange
+    auto epi_bar = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     auto sw = [&](uint8_t* base, int row, int chunk) -> uint4* {
       return reinterpret_cast<uint4*>(base + row * 128 + ((chunk ^ (row & 7)) << 4));
     };
@@ -249,7 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     };
 
     if (p.mode == EPI_PLAIN || p.mode == EPI_QKV) {
-      for (int dc = 0; dc < BLOCK_N / 64; ++dc) {
+      for (int dc = half; dc < BLOCK_N / 64; dc += 2) {
         const int n0 = n_tile * BLOCK_N + dc * 64;
         if (n0 >= p.N) break;
         const int nvalid = min(64, p.N - n0);
@@ -352,15 +364,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     } else if (p.mode == EPI_LN) {
       // pass A: x = acc + bias + residual, row sums, x written back to TMEM
       float sum = 0.f;
-      for (int dc = 0; dc < BLOCK_N / 64; ++dc) {
-        const int n0 = dc * 64;
+      const int nbase = n_tile * BLOCK_N;            // column offset of this CTA (cluster split of N)
+      const float inv_n = 1.f / static_cast<float>(p.ln_cluster ? 2 * BLOCK_N : BLOCK_N);
+      const uint32_t peer = cluster_ctarank() ^ 1u;
+      for (int dc = half; dc < BLOCK_N / 64; dc += 2) {
+        const int n0 = nbase + dc * 64;
         __syncwarp();
         if (p.residual) {
           load_f32_slab(s_res, p.residual, p.res_ld, n0, 64);
           load_f32_slab(s_res + 4096, p.residual, p.res_ld, n0 + 32, 32);
         }
-        tmem_ld32(taddr + n0, v);
-        tmem_ld32(taddr + n0 + 32, w);
+        tmem_ld32(taddr + dc * 64, v);
+        tmem_ld32(taddr + dc * 64 + 32, w);
         tmem_wait_ld();
         __syncwarp();
 #pragma unroll
@@ -385,30 +400,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int e = 0; e < 4; ++e) acc[g * 4 + e] = __float_as_uint(x[e]);
           }
         }
-        tmem_st32(taddr + n0, v);
-        tmem_st32(taddr + n0 + 32, w);
+        tmem_st32(taddr + dc * 64, v);
+        tmem_st32(taddr + dc * 64 + 32, w);
       }
       tmem_wait_st();
-      const float mean = sum * (1.f / BLOCK_N);
-      // pass B: centred second moment (TMEM reads only)
+      red[half * 128 + r] = sum;                     // combine the two column halves of every row
+      tc_fence_before();
+      epi_bar();
+      tc_fence_after();
+      float tot = sum + red[(half ^ 1) * 128 + r];
+      if (p.ln_cluster) {                            // push this CTA's row sums into the peer, wait for the peer's
+        if (half == 0) {
+          st_cluster_f32(map_to_cta(smem_u32(&xred[r]), peer), tot);
+          mbar_arrive_cluster(map_to_cta(smem_u32(&xbar[0]), peer));
+        }
+        mbar_wait_cluster(&xbar[0], 0);
+        tot += xred[r];
+      }
+      const float mean = tot * inv_n;
+      // pass B: centred second moment (TMEM reads only), this warp's chunks
       float sq4[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = 2 * half; c < BLOCK_N / 32; c += 4) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
         __syncwarp();
-        tmem_ld32(taddr + c * 32, v);
+        tmem_ld32(taddr + (c + cc) * 32, v);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float d = __uint_as_float(v[j]) - mean;
           sq4[j & 3] = fmaf(d, d, sq4[j & 3]);
         }
+        }
       }
-      const float rstd = 1.f / sqrtf(((sq4[0] + sq4[1]) + (sq4[2] + sq4[3])) * (1.f / BLOCK_N) + p.ln_eps);
+      const float sq_part = (sq4[0] + sq4[1]) + (sq4[2] + sq4[3]);
+      epi_bar();                                     // everyone has consumed the first exchange
+      red[half * 128 + r] = sq_part;
+      epi_bar();
+      float sqt = sq_part + red[(half ^ 1) * 128 + r];
+      if (p.ln_cluster) {
+        if (half == 0) {
+          st_cluster_f32(map_to_cta(smem_u32(&xred[128 + r]), peer), sqt);
+          mbar_arrive_cluster(map_to_cta(smem_u32(&xbar[1]), peer));
+        }
+        mbar_wait_cluster(&xbar[1], 0);
+        sqt += xred[128 + r];
+      }
+      const float rstd = 1.f / sqrtf(sqt * inv_n + p.ln_eps);
       // pass C: normalise, gamma/beta, stage, coalesced copy-out
-      for (int dc = 0; dc < BLOCK_N / 64; ++dc) {
-        const int n0 = dc * 64;
+      for (int dc = half; dc < BLOCK_N / 64; dc += 2) {
+        const int n0 = nbase + dc * 64;
         __syncwarp();
-        tmem_ld32(taddr + n0, v);
-        tmem_ld32(taddr + n0 + 32, w);
+        tmem_ld32(taddr + dc * 64, v);
+        tmem_ld32(taddr + dc * 64 + 32, w);
         tmem_wait_ld();
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -447,7 +491,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         if (p.out_h) store_f16_slab(s_h, p.out_h, p.ld_h, n0, 64);
       }
-    } else if (p.mode == EPI_COUPLING) {
+    } else if (p.mode == EPI_COUPLING && half == 0) {
       // columns [0, half) = log_scale, [half, 2*half) = shift, half = N / 2 (modules/flow.py:223-257).
       // Per 32 latent channels: T[row][0..31] = log_scale, T[row][32..63] = shift; lane == channel.
       const int half = p.N >> 1;
@@ -485,7 +529,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
       if (row_ok) p.row_acc[grow] += in_len ? (p.backward ? -logdet : logdet) : 0.f;
-    } else if (p.mode == EPI_POSTERIOR) {
+    } else if (p.mode == EPI_POSTERIOR && half == 0) {
       // modules/posterior.py:20-72 with the models.py:136 name swap already applied by the packing order:
       // columns [0, L) = log-variance (mu_projection), [L, 2L) = mean (logvar_projection), L = N / 2.
       const int L = p.N >> 1;
@@ -530,6 +574,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+  if (p.ln_cluster) cluster_sync_all();   // no CTA of the pair exits while the other may still address its shared memory
 }
 
 }  // namespace vb
