@@ -84,13 +84,25 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def usable_cores():
+    """Host cores this process may really use: min(affinity, cgroup CPU quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_oracle_time(steps, warmup, batch):
     """Times the reference's CPU implementation of the path (the oracle port, PyTorch eager fp32) on the host
     cores.  The ONLY place bench.py executes oracle/."""
     import torch
     from oracle import vaenar_oracle as O
     from oracle.hparams import LJHPS as OH
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     P = O.init_params(OH, seed=OH.Train.random_seed)
     texts, mels, t_len, m_len = O.synthetic_batch(OH, batch, T_TEXT, T_MEL)

@@ -1360,6 +1360,12 @@ int vaenar_randn(float* out, int64_t n, uint64_t seed, uint64_t stream_id, float
 
 long vaenar_launch_count(void) { return g_launch_count; }
 
+// Debug/tuning: device buffer (8 x u64 per CTA) receiving per-phase globaltimer stamps of every GEMM CTA; null disables.
+int vaenar_debug_gemm_timestamps(void* dev_buf) {
+  unsigned long long* p = static_cast<unsigned long long*>(dev_buf);
+  return cudaMemcpyToSymbol(g_gemm_dbg, &p, sizeof(p)) == cudaSuccess ? 0 : -1;
+}
+
 // Enable (1) / disable (0) per-launch CUDA-event timing of the tensor-core kernels.  Not for use during
 // graph capture.  vaenar_profile_report() synchronises the device and returns a JSON object
 // {class: {launches, ms, flops, bytes}} for the launches seen since the last enable.

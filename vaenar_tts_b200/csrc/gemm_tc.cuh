@@ -100,6 +100,14 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// optional in-kernel phase timestamps (debug / tuning only): 8 x u64 per CTA, globaltimer ns
+__device__ unsigned long long* g_gemm_dbg = nullptr;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -117,6 +125,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* xbar = bars + 2 * Cfg::kStages + 2;             // [2] cluster LayerNorm exchange
   float* xred = reinterpret_cast<float*>(bars + 2 * Cfg::kStages + 4);   // [2][128] written by the peer CTA
 
+  unsigned long long* dbg = g_gemm_dbg ? g_gemm_dbg + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 64) dbg[0] = gtime();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x;
@@ -148,6 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (p.ln_cluster) cluster_sync_all();   // peer barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 64) dbg[1] = gtime();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -215,6 +226,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (dbg && threadIdx.x == 64) dbg[2] = gtime();
     uint32_t v[32], w[32];
 
     // Warp-private staging slabs (the pipeline stages are idle now): 32 rows x 128 B, 16-byte chunks
@@ -568,8 +580,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (row_ok) p.row_acc[grow] += in_len ? -0.5f * (static_cast<float>(L) * 1.8378770664093453f + acc) : 0.f;
     }
     tc_fence_before();
+    if (dbg && threadIdx.x == 64) dbg[3] = gtime();
   }
   __syncthreads();
+  if (dbg && threadIdx.x == 64) dbg[4] = gtime();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
