@@ -221,8 +221,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const long grow0 = static_cast<long>(tile_b) * p.rows + tile_t0 + quad * 32;   // first row of this warp
     const int rows_here = min(32, p.rows - (tile_t0 + quad * 32));                  // valid rows of this warp (may be <= 0)
-    constexpr int TS = 65;
-    float* T = reinterpret_cast<float*>(smem_a + (warp - 2) * (4 * 4096));   // 8320 B of this warp's 16 KB
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
@@ -251,7 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int row = it * 4 + (lane >> 3), chunk = lane & 7;
         uint4 u = make_uint4(0u, 0u, 0u, 0u);
         if (row < rows_here && chunk * 4 < ncols_valid)
-          u = __ldg(reinterpret_cast<const uint4*>(g + (grow0 + row) * ld + col0 + chunk * 4));
+          u = *reinterpret_cast<const uint4*>(g + (grow0 + row) * ld + col0 + chunk * 4);   // plain load: z is updated in place
         *sw(base, row, chunk) = u;
       }
     };
@@ -503,81 +501,113 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         if (p.out_h) store_f16_slab(s_h, p.out_h, p.ld_h, n0, 64);
       }
-    } else if (p.mode == EPI_COUPLING && half == 0) {
-      // columns [0, half) = log_scale, [half, 2*half) = shift, half = N / 2 (modules/flow.py:223-257).
-      // Per 32 latent channels: T[row][0..31] = log_scale, T[row][32..63] = shift; lane == channel.
-      const int half = p.N >> 1;
+    } else if (p.mode == EPI_COUPLING) {
+      // columns [0, hN) = log_scale, [hN, 2 hN) = shift, hN = N / 2 = 64 (modules/flow.py:223-257).
+      // Each warp half owns 32 of the 64 transformed channels; z is staged through the swizzled slabs.
+      const int hN = p.N >> 1;
+      const int ch0 = half * 32;
       const int len_b = __ldg(p.lengths + min(sb, p.seq_B - 1));
       const bool in_len = row_ok && (st < len_b);
-      float logdet = 0.f;
-      for (int c = 0; c < half / 32; ++c) {
-        __syncwarp();
-        tmem_ld32(taddr + c * 32, v);
-        tmem_ld32(taddr + half + c * 32, w);
-        tmem_wait_ld();
+      __syncwarp();
+      load_f32_slab(s_res, p.z, p.z_ld, p.zp_off + ch0, 32);
+      tmem_ld32(taddr + ch0, v);
+      tmem_ld32(taddr + hN + ch0, w);
+      tmem_wait_ld();
+      __syncwarp();
+      float ld4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          T[lane * TS + j] = __uint_as_float(v[j]);
-          T[lane * TS + 32 + j] = __uint_as_float(w[j]);
-        }
-        __syncwarp();
-        const int ch = c * 32 + lane;
-        const float bl = __ldg(p.bias + ch), bs = __ldg(p.bias + half + ch);
-        for (int i = 0; i < rows_here; ++i) {
-          const long gr = grow0 + i;
-          const float ls = T[i * TS + lane] + bl;
-          const float sh = T[i * TS + 32 + lane] + bs;
+      for (int g = 0; g < 8; ++g) {
+        const float4 bl = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + g * 4));
+        const float4 bs = __ldg(reinterpret_cast<const float4*>(p.bias + hN + ch0 + g * 4));
+        const uint4 zq = *sw(s_res, lane, g);
+        const float zp[4] = {__uint_as_float(zq.x), __uint_as_float(zq.y), __uint_as_float(zq.z), __uint_as_float(zq.w)};
+        const float lsb[4] = {bl.x, bl.y, bl.z, bl.w}, shb[4] = {bs.x, bs.y, bs.z, bs.w};
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float ls = __uint_as_float(v[g * 4 + e]) + lsb[e];
+          const float sh = __uint_as_float(w[g * 4 + e]) + shb[e];
           const float scale = 1.f / (1.f + expf(-(ls + 2.0f)));
-          float* zp = p.z + gr * p.z_ld + p.zp_off + ch;
-          const float o = p.backward ? (*zp - sh) / (scale + 1e-12f) : scale * (*zp) + sh;
-          *zp = o;
-          p.z_h[gr * p.z_ld + p.zp_off + ch] = __float2half_rn(o);
-          T[i * TS + lane] = logf(scale);
+          o[e] = p.backward ? (zp[e] - sh) / (scale + 1e-12f) : scale * zp[e] + sh;
+          ld4[e] += logf(scale);
+          v[g * 4 + e] = __float_as_uint(o[e]);
         }
-        __syncwarp();
-        if (row_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) logdet += T[lane * TS + j];
-        }
+        *sw(s_f32, lane, g) = make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]),
+                                         __float_as_uint(o[3]));
       }
-      if (row_ok) p.row_acc[grow] += in_len ? (p.backward ? -logdet : logdet) : 0.f;
-    } else if (p.mode == EPI_POSTERIOR && half == 0) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 u;
+        u.x = pack_half2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+        u.y = pack_half2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+        u.z = pack_half2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+        u.w = pack_half2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+        *sw(s_h, lane, g) = u;
+      }
+      __syncwarp();
+      store_f32_slab(s_f32, p.z, p.z_ld, p.zp_off + ch0, 32);
+      store_f16_slab(s_h, p.z_h, p.z_ld, p.zp_off + ch0, 32);
+      const float logdet = (ld4[0] + ld4[1]) + (ld4[2] + ld4[3]);
+      red[half * 128 + r] = logdet;
+      epi_bar();
+      if (half == 0 && row_ok) {
+        const float tot = logdet + red[128 + r];
+        p.row_acc[grow] += in_len ? (p.backward ? -tot : tot) : 0.f;
+      }
+    } else if (p.mode == EPI_POSTERIOR) {
       // modules/posterior.py:20-72 with the models.py:136 name swap already applied by the packing order:
       // columns [0, L) = log-variance (mu_projection), [L, 2L) = mean (logvar_projection), L = N / 2.
       const int L = p.N >> 1;
       const int len_b = __ldg(p.lengths + min(sb, p.seq_B - 1));
       const bool in_len = row_ok && (st < len_b);
-      float acc = 0.f;
-      for (int c = 0; c < L / 32; ++c) {
+      float a4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int c = half; c < L / 32; c += 2) {
+        const int ch0 = c * 32;
         __syncwarp();
-        tmem_ld32(taddr + c * 32, v);
-        tmem_ld32(taddr + L + c * 32, w);
+        load_f32_slab(s_res, p.eps_in, p.z_ld, ch0, 32);
+        tmem_ld32(taddr + ch0, v);
+        tmem_ld32(taddr + L + ch0, w);
         tmem_wait_ld();
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          T[lane * TS + j] = __uint_as_float(v[j]);
-          T[lane * TS + 32 + j] = __uint_as_float(w[j]);
+        for (int g = 0; g < 8; ++g) {
+          const float4 bl = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + g * 4));
+          const float4 bm = __ldg(reinterpret_cast<const float4*>(p.bias + L + ch0 + g * 4));
+          const uint4 eq = *sw(s_res, lane, g);
+          const float ee[4] = {__uint_as_float(eq.x), __uint_as_float(eq.y), __uint_as_float(eq.z), __uint_as_float(eq.w)};
+          const float lvb[4] = {bl.x, bl.y, bl.z, bl.w}, mub[4] = {bm.x, bm.y, bm.z, bm.w};
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float lv = __uint_as_float(v[g * 4 + e]) + lvb[e];
+            const float mu = __uint_as_float(w[g * 4 + e]) + mub[e];
+            o[e] = ee[e] * expf(0.5f * lv) + mu;
+            a4[e] += lv + ee[e] * ee[e];
+            v[g * 4 + e] = __float_as_uint(o[e]);
+          }
+          *sw(s_f32, lane, g) = make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]),
+                                           __float_as_uint(o[3]));
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_half2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+          u.y = pack_half2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+          u.z = pack_half2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+          u.w = pack_half2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+          *sw(s_h, lane, g) = u;
         }
         __syncwarp();
-        const int ch = c * 32 + lane;
-        const float bl = __ldg(p.bias + ch), bm = __ldg(p.bias + L + ch);
-        for (int i = 0; i < rows_here; ++i) {
-          const long gr = grow0 + i;
-          const float lv = T[i * TS + lane] + bl;
-          const float mu = T[i * TS + 32 + lane] + bm;
-          const float e = __ldg(p.eps_in + gr * p.z_ld + ch);
-          const float o = e * expf(0.5f * lv) + mu;
-          p.z[gr * p.z_ld + ch] = o;
-          p.z_h[gr * p.z_ld + ch] = __float2half_rn(o);
-          T[i * TS + lane] = lv + e * e;
-        }
-        __syncwarp();
-        if (row_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc += T[lane * TS + j];
-        }
+        store_f32_slab(s_f32, p.z, p.z_ld, ch0, 32);
+        store_f16_slab(s_h, p.z_h, p.z_ld, ch0, 32);
       }
-      if (row_ok) p.row_acc[grow] += in_len ? -0.5f * (static_cast<float>(L) * 1.8378770664093453f + acc) : 0.f;
+      const float acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+      red[half * 128 + r] = acc;
+      epi_bar();
+      if (half == 0 && row_ok) {
+        const float tot = acc + red[128 + r];
+        p.row_acc[grow] += in_len ? -0.5f * (static_cast<float>(L) * 1.8378770664093453f + tot) : 0.f;
+      }
     }
     tc_fence_before();
     if (dbg && threadIdx.x == 64) dbg[3] = gtime();
