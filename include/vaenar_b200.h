@@ -125,6 +125,7 @@ int vaenar_profile_enable(int on);
 const char* vaenar_profile_report(void);
 /* Tuning aid: per-CTA phase timestamps (8 x u64, globaltimer ns) of the GEMM kernel into dev_buf; NULL disables. */
 int vaenar_debug_gemm_timestamps(void* dev_buf);
+const char* vaenar_debug_gemm_launches(void);
 
 /* ---- block-level entry points (parity tests of single kernels against the oracle) ---- */
 /* out = act(A[M,K] W[K,N] + bias) (+residual, LayerNorm if ln != 0); A, W fp32 host-layout device buffers;

@@ -54,6 +54,7 @@ _SIGS = {
     "vaenar_profile_enable": (c_int, [c_int]),
     "vaenar_profile_report": (c_char_p, []),
     "vaenar_debug_gemm_timestamps": (c_int, [_P]),
+    "vaenar_debug_gemm_launches": (c_char_p, []),
     "vaenar_test_dense": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P,
                                   c_int64, _P]),
     "vaenar_test_conv1d": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),

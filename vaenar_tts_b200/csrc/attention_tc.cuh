@@ -18,8 +18,9 @@
 //
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 softmax: two warps per TMEM lane
 // quadrant, each owning one 64-key panel of every 128-key block (row statistics combined through shared memory).
-// Key blocks that cannot contribute are skipped: above the causal diagonal, or beyond key_len, unless the query
-// tile contains fully masked rows (which attend uniformly to ALL keys).
+// Key blocks that cannot contribute to a LIVE row are skipped (above the causal diagonal, beyond key_len).  Fully
+// masked rows attend uniformly to all T_k keys, i.e. their context is the column mean of V: tiles that contain such
+// rows compute that mean once from V^T (fp32) and write it directly, so dead rows / dead tiles cost no MMA work.
 #pragma once
 #include "ptx.cuh"
 
@@ -34,13 +35,15 @@ constexpr int ATT_QBYTES = ATT_BQ * ATT_D * 2;       // 16 KB
 constexpr int ATT_KBYTES = ATT_BK * ATT_D * 2;       // 16 KB
 constexpr int ATT_VBYTES = ATT_D * ATT_BK * 2;       // 16 KB (two 64-key panels of 8 KB)
 constexpr int ATT_PBYTES = ATT_BQ * ATT_BK * 2;      // 32 KB (two 64-key panels of 16 KB)
-constexpr int ATT_SMEM = ATT_QBYTES + 2 * ATT_KBYTES + 2 * ATT_VBYTES + 2 * ATT_PBYTES + 256 + 3 * 2 * ATT_BQ * 4 + 1024;
+constexpr int ATT_SMEM = ATT_QBYTES + 2 * ATT_KBYTES + 2 * ATT_VBYTES + 2 * ATT_PBYTES + 256 + 3 * 2 * ATT_BQ * 4 + 256 + 1024;
 
 struct AttnParams {
   int B, H, Tq, Tk;
   int q_col0;            // column of head 0 inside the Q tensor map
   int k_col0;            // column of head 0 inside the K tensor map
   long vt_row0;          // first V^T row of (batch 0, head 0) for this block
+  const __half* vt;      // V^T base pointer and row pitch (for the column mean used by fully masked rows)
+  int vt_ld;
   const int* q_len;      // [B]
   const int* k_len;      // [B]
   int causal;
@@ -81,17 +84,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int b = blockIdx.z;
   const int qlen = __ldg(p.q_len + b);
   const int klen = __ldg(p.k_len + b);
-  // key blocks that can contribute to this query tile (identical in every warp role)
-  int nblk = (p.Tk + ATT_BK - 1) / ATT_BK;
-  {
-    const int q_hi = min(q0 + ATT_BQ, p.Tq);
-    const bool has_dead_rows = max(q0, qlen) < q_hi || klen <= 0;   // fully masked rows need all Tk keys
-    if (!has_dead_rows) {
-      nblk = min(nblk, (klen + ATT_BK - 1) / ATT_BK);
-      if (p.causal) nblk = min(nblk, (q_hi - 1) / ATT_BK + 1);
-    }
+  // key blocks that can contribute to the LIVE rows of this query tile (identical in every warp role)
+  const int q_hi = min(q0 + ATT_BQ, p.Tq);
+  const bool has_dead_rows = max(q0, qlen) < q_hi || klen <= 0;   // some stored row is fully masked
+  const bool all_dead = q0 >= qlen || klen <= 0;                   // every stored row is fully masked
+  int nblk = 0;
+  if (!all_dead) {
+    nblk = min((p.Tk + ATT_BK - 1) / ATT_BK, (klen + ATT_BK - 1) / ATT_BK);
+    if (p.causal) nblk = min(nblk, (min(q_hi, qlen) - 1) / ATT_BK + 1);
   }
-
+  float* vmean = red + 6 * ATT_BQ;   // [64] column mean of V for fully masked rows
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -122,7 +124,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (elect_one()) {
+    if (nblk > 0 && elect_one()) {
       mbar_arrive_expect_tx(q_full, ATT_QBYTES);
       tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + h * ATT_D, q0, b);
       const long vrow = p.vt_row0 + (static_cast<long>(b) * p.H + h) * ATT_D;
@@ -145,7 +147,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (elect_one()) {
+    if (nblk > 0 && elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_f16(ATT_BQ, ATT_BK);   // S: 128 x 128, K = 64
       constexpr uint32_t idesc_o = umma_idesc_f16(ATT_BQ, ATT_D);    // O: 128 x 64,  K = 128
       auto issue_pv = [&](int iv) {
@@ -197,6 +199,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const float inv_tk = 1.0f / static_cast<float>(p.Tk);
     uint32_t v[32];
     auto softmax_bar = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+
+    if (has_dead_rows) {
+      // column mean of V over ALL Tk padded keys (the uniform distribution of attention.py:240-242), fp32
+      const int sidx = (warp - 2) * 32 + lane;      // 0..255: 4 threads per head channel
+      const int d = sidx >> 2, part = sidx & 3;
+      const __half* vrow = p.vt + (p.vt_row0 + (static_cast<long>(b) * p.H + h) * ATT_D + d) * p.vt_ld;
+      float acc = 0.f;
+      for (int t0 = part * 8; t0 < p.Tk; t0 += 32) {
+        if (t0 + 8 <= p.Tk) {
+          const uint4 u = *reinterpret_cast<const uint4*>(vrow + t0);
+          const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(hp[e]);
+            acc += f.x + f.y;
+          }
+        } else {
+          for (int t = t0; t < p.Tk; ++t) acc += __half2float(vrow[t]);
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (part == 0) vmean[d] = acc * inv_tk;
+    }
 
     // ---- pass 1: row maximum (and denominator if the alignments are written)
     float m = -INFINITY;
@@ -277,13 +303,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const int kk = kk0 + e;
           float pe;
           if (row_dead) {
-            pe = (kk < p.Tk) ? inv_tk : 0.f;
+            pe = 0.f;                 // dead rows take the V column mean directly (epilogue)
           } else {
             const bool ok = (kk < klen) && (!p.causal || kk <= q);
             pe = ok ? ex2_approx(__uint_as_float(v[e]) * sl2 - msl2) : 0.f;
           }
           ls[e & 3] += pe;
           pr[e] = pe * inv_l;           // normalised already when kWriteAli (inv_l == 1 otherwise)
+          if (kWriteAli && row_dead) pr[e] = (kk < p.Tk) ? inv_tk : 0.f;   // alignments of a dead row: uniform
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -293,6 +320,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           u.y = pack_half2(pr[g * 8 + 2], pr[g * 8 + 3]);
           u.z = pack_half2(pr[g * 8 + 4], pr[g * 8 + 5]);
           u.w = pack_half2(pr[g * 8 + 6], pr[g * 8 + 7]);
+          if (row_dead) u = make_uint4(0u, 0u, 0u, 0u);
           *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = u;
         }
         if (kWriteAli && row_store) {
@@ -305,11 +333,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_arrive(&p_full[sp]);
       mbar_arrive(&s_empty[st]);
     }
-    // alignments of skipped key blocks are exact zeros (they only exist when the tile has no dead rows)
+    // alignments of skipped key blocks: exact zeros for live rows, uniform 1/Tk for fully masked rows
     if (kWriteAli && row_store) {
       const int k_done = nblk * ATT_BK;
       float* arow = p.ali + ((static_cast<long>(b) * p.H + h) * p.Tq + q) * p.Tk;
-      for (int kk = k_done + half; kk < p.Tk; kk += 2) arow[kk] = 0.f;
+      const float fill = row_dead ? inv_tk : 0.f;
+      for (int kk = k_done + half; kk < p.Tk; kk += 2) arow[kk] = fill;
     }
 
     // ---- epilogue: ctx = O / l ; each half handles 32 of the 64 head channels
@@ -317,21 +346,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     red[4 * ATT_BQ + half * ATT_BQ + r] = lsum;
     softmax_bar();
     lsum += red[4 * ATT_BQ + (half ^ 1) * ATT_BQ + r];
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    const float on = kWriteAli ? 1.0f : 1.0f / lsum;
-    __syncwarp();
-    tmem_ld32(tmem_O + lane_off + half * 32, v);
-    tmem_wait_ld();
+    if (nblk > 0) {
+      mbar_wait(o_full, 0);
+      tc_fence_after();
+      __syncwarp();
+      tmem_ld32(tmem_O + lane_off + half * 32, v);
+      tmem_wait_ld();
+    }
+    const float on = row_dead ? 0.f : (kWriteAli ? 1.0f : 1.0f / lsum);
     if (row_store) {
       __half* dst = p.ctx + (static_cast<long>(b) * p.Tq + q) * p.ctx_ld + h * ATT_D + half * 32;
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          f[e] = row_dead ? vmean[half * 32 + j + e] : __uint_as_float(v[j + e]) * on;
         uint4 u;
-        u.x = pack_half2(__uint_as_float(v[j]) * on, __uint_as_float(v[j + 1]) * on);
-        u.y = pack_half2(__uint_as_float(v[j + 2]) * on, __uint_as_float(v[j + 3]) * on);
-        u.z = pack_half2(__uint_as_float(v[j + 4]) * on, __uint_as_float(v[j + 5]) * on);
-        u.w = pack_half2(__uint_as_float(v[j + 6]) * on, __uint_as_float(v[j + 7]) * on);
+        u.x = pack_half2(f[0], f[1]);
+        u.y = pack_half2(f[2], f[3]);
+        u.z = pack_half2(f[4], f[5]);
+        u.w = pack_half2(f[6], f[7]);
         *reinterpret_cast<uint4*>(dst + j) = u;
       }
     }

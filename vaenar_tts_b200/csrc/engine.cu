@@ -448,6 +448,9 @@ struct KernelStat {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
 };
 static long g_launch_count = 0;
+static unsigned long long* g_dbg_cursor = nullptr;   // tuning aid: per-CTA phase timestamps of GEMM launches
+static unsigned long long* g_dbg_base = nullptr;
+static std::vector<std::string> g_dbg_launches;
 static bool g_profile = false;
 static std::map<std::string, KernelStat> g_stats;
 static std::string g_profile_json;
@@ -478,12 +481,28 @@ struct ProfileScope {
   }
 };
 
+#define VB_GEMM_INSTANCES(X)                                                                       \
+  X(128, EPI_PLAIN, F_RUNTIME) X(256, EPI_PLAIN, F_RUNTIME)                                          \
+  X(128, EPI_PLAIN, F_OUT_H) X(128, EPI_PLAIN, F_BIAS | F_RELU | F_OUT_H)                             \
+  X(128, EPI_PLAIN, F_BIAS | F_TABLE | F_OUT_F32 | F_OUT_H)                                           \
+  X(128, EPI_PLAIN, F_BIAS | F_RELU | F_BN | F_OUT_H)                                                 \
+  X(128, EPI_PLAIN, F_BIAS | F_TANH | F_BN | F_OUT_H | F_OUT_LO)                                      \
+  X(128, EPI_PLAIN, F_BIAS | F_BN | F_OUT_H | F_OUT_LO)                                               \
+  X(128, EPI_PLAIN, F_BIAS | F_OUT_F32 | F_OUT_H)                                                     \
+  X(128, EPI_PLAIN, F_BIAS | F_RELU | F_TABLE | F_OUT_F32 | F_OUT_H)                                  \
+  X(128, EPI_PLAIN, F_BIAS | F_OUT_F32 | F_OUT_H | F_OUT_LO)                                          \
+  X(128, EPI_PLAIN, F_BIAS | F_RES | F_OUT_F32)                                                       \
+  X(128, EPI_LN, 0) X(256, EPI_LN, 0) X(512, EPI_LN, 0)                                              \
+  X(256, EPI_QKV, F_OUT_H) X(128, EPI_COUPLING, 0) X(256, EPI_POSTERIOR, 0)
+
 static void set_attrs(vaenar_model* m) {
   static bool done = false;
   if (done) return;
-  VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes));
-  VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmemBytes));
-  VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<512>::kSmemBytes));
+#define VB_SET_ATTR(BN, MODE, FEAT)                                                                  \
+  VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, (FEAT)>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               GemmCfg<BN>::kSmemBytes));
+  VB_GEMM_INSTANCES(VB_SET_ATTR)
+#undef VB_SET_ATTR
   VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   VB_CUDA(cudaFuncSetAttribute(slogdet128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOW_DIM * (FLOW_DIM + 1) * 8));
@@ -532,6 +551,8 @@ static void run_gemm(Ctx& c, int block_n, AOp a0, AOp a1, int batches, int rows,
   int tk = 0;
   for (int s = 0; s < p.nseg; ++s) tk += p.seg_kblocks[s];
   if (tk * 64 != Ktot) VB_THROW("gemm: segments cover %d of K %d", tk * 64, Ktot);
+  if (p.mode == EPI_LN && !(p.bias && p.residual && p.out_f32 && p.out_h && p.ln_gamma && p.ln_beta))
+    VB_THROW("gemm: the LayerNorm epilogue needs bias, residual, gamma, beta and both outputs");
   // LayerNorm over N = 2 * BLOCK_N: split the columns over a 2-CTA cluster (row statistics via DSMEM)
   p.ln_cluster = (p.mode == EPI_LN && p.N == 2 * block_n) ? 1 : 0;
   if ((p.mode == EPI_LN && !p.ln_cluster && p.N != block_n) ||
@@ -548,6 +569,15 @@ static void run_gemm(Ctx& c, int block_n, AOp a0, AOp a1, int batches, int rows,
   dim3 grid(batches * p.tiles_per_batch, cdiv(p.N, block_n));
   const double Mrows = static_cast<double>(batches) * rows;
   const double kalg = p.alg_k > 0 ? p.alg_k : Ktot;   // algorithmic K: no padding, no split-fp16 triple
+  if (g_dbg_cursor) {
+    if (g_dbg_launches.empty()) g_dbg_base = g_dbg_cursor;
+    p.dbg = g_dbg_cursor;
+    char buf[256];
+    snprintf(buf, sizeof(buf), "{\"grid\": [%u, %u], \"mode\": %d, \"N\": %d, \"K\": %d, \"bn\": %d, \"offset\": %lld}", grid.x, grid.y, p.mode, p.N, Ktot,
+             block_n, static_cast<long long>(g_dbg_cursor - g_dbg_base));
+    g_dbg_launches.push_back(buf);
+    g_dbg_cursor += static_cast<size_t>(grid.x) * grid.y * 8;
+  }
   const char* cls = p.mode == EPI_LN ? "gemm_ln" : (p.nseg >= 5 ? "gemm_conv" : (p.mode == EPI_QKV ? "gemm_qkv" : "gemm_plain"));
   ProfileScope prof(cls, 2.0 * Mrows * p.N * kalg, Mrows * kalg * 2 + static_cast<double>(p.N) * Ktot * 2 + Mrows * p.N * 6, c.stream);
   cudaLaunchConfig_t cfg;
@@ -562,13 +592,32 @@ static void run_gemm(Ctx& c, int block_n, AOp a0, AOp a1, int batches, int rows,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le;
-  switch (block_n) {
-    case 128: cfg.dynamicSmemBytes = GemmCfg<128>::kSmemBytes; le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<128>, tA0, tA1, tB, p); break;
-    case 256: cfg.dynamicSmemBytes = GemmCfg<256>::kSmemBytes; le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256>, tA0, tA1, tB, p); break;
-    case 512: cfg.dynamicSmemBytes = GemmCfg<512>::kSmemBytes; le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<512>, tA0, tA1, tB, p); break;
-    default: VB_THROW("unsupported BLOCK_N %d", block_n);
+  cudaError_t le = cudaErrorInvalidValue;
+  bool launched = false;
+  // feature mask of this call (EPI_PLAIN); a specialised instance is used when one exists, else the run-time one
+  uint32_t feat = 0;
+  if (p.mode == EPI_PLAIN) {
+    feat = (p.bias ? F_BIAS : 0) | (p.act == 1 ? F_RELU : 0) | (p.act == 2 ? F_TANH : 0) | (p.ch_scale ? F_BN : 0) |
+           (p.add_table ? F_TABLE : 0) | (p.residual ? F_RES : 0) | (p.out_f32 ? F_OUT_F32 : 0) | (p.out_h ? F_OUT_H : 0) |
+           (p.out_lo ? F_OUT_LO : 0);
   }
+#define VB_TRY(BN, MODE, FEAT)                                                                              \
+  if (!launched && block_n == BN && p.mode == MODE && (MODE != EPI_PLAIN || feat == static_cast<uint32_t>(FEAT))) { \
+    cfg.dynamicSmemBytes = GemmCfg<BN>::kSmemBytes;                                                         \
+    le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, (FEAT)>, tA0, tA1, tB, p);                       \
+    launched = true;                                                                                        \
+  }
+#define VB_TRY_RT(BN, MODE, FEAT)                                                                           \
+  if (!launched && block_n == BN && p.mode == MODE && MODE == EPI_PLAIN && ((FEAT) & F_RUNTIME)) {          \
+    cfg.dynamicSmemBytes = GemmCfg<BN>::kSmemBytes;                                                         \
+    le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, (FEAT)>, tA0, tA1, tB, p);                       \
+    launched = true;                                                                                        \
+  }
+  VB_GEMM_INSTANCES(VB_TRY)
+  VB_GEMM_INSTANCES(VB_TRY_RT)
+#undef VB_TRY
+#undef VB_TRY_RT
+  if (!launched) VB_THROW("no gemm_tc_kernel instance for BLOCK_N %d mode %d", block_n, p.mode);
   if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(gemm_tc_kernel<%d>) failed: %s", block_n, cudaGetErrorString(le));
   check_launch("gemm_tc_kernel");
 }
@@ -594,6 +643,7 @@ static void run_attention(Ctx& c, int B, int H, const AttnCall& a) {
   AttnParams p;
   p.B = B; p.H = H; p.Tq = a.Tq; p.Tk = a.Tk;
   p.q_col0 = a.q_col0; p.k_col0 = a.k_col0; p.vt_row0 = a.vt_row0;
+  p.vt = a.vt; p.vt_ld = a.vt_ld;
   p.q_len = a.q_len; p.k_len = a.k_len; p.causal = a.causal;
   p.scale = 1.0f / sqrtf(static_cast<float>(ATT_D));   // attention.py:227-229, temperature 1.0
   p.ctx = a.ctx; p.ctx_ld = a.ctx_ld; p.ali = a.ali;
@@ -1362,8 +1412,17 @@ long vaenar_launch_count(void) { return g_launch_count; }
 
 // Debug/tuning: device buffer (8 x u64 per CTA) receiving per-phase globaltimer stamps of every GEMM CTA; null disables.
 int vaenar_debug_gemm_timestamps(void* dev_buf) {
-  unsigned long long* p = static_cast<unsigned long long*>(dev_buf);
-  return cudaMemcpyToSymbol(g_gemm_dbg, &p, sizeof(p)) == cudaSuccess ? 0 : -1;
+  g_dbg_cursor = static_cast<unsigned long long*>(dev_buf);
+  g_dbg_launches.clear();
+  return 0;
+}
+// JSON list of the GEMM launches recorded since the buffer was set: [{"grid": [x, y], "cls": ..., "offset": u64 index}]
+const char* vaenar_debug_gemm_launches(void) {
+  static std::string out;
+  out = "[";
+  for (size_t i = 0; i < g_dbg_launches.size(); ++i) out += (i ? ", " : "") + g_dbg_launches[i];
+  out += "]";
+  return out.c_str();
 }
 
 // Enable (1) / disable (0) per-launch CUDA-event timing of the tensor-core kernels.  Not for use during
@@ -1449,6 +1508,7 @@ int vaenar_test_dense(const float* A, const float* W, const float* bias, const f
   GemmParams p = gp();
   p.mode = ln ? EPI_LN : EPI_PLAIN; p.N = N; p.act = act; p.bias = bias; p.residual = residual; p.res_ld = N;
   p.ln_gamma = gamma; p.ln_beta = beta; p.out_f32 = out; p.ld_f32 = N;
+  if (ln) { p.out_h = c.alloc<__half>(static_cast<int64_t>(M) * N); p.ld_h = N; }
   p.nseg = parts;
   for (int q = 0; q < parts; ++q) { p.seg_map[q] = (q == 1) ? 1 : 0; p.seg_shift[q] = 0; p.seg_kblocks[q] = Kp / 64; }
   run_gemm(c, block_n, AOp{Ah, K, K}, AOp{split ? Al : nullptr, K, K}, 1, M, Wp, parts * Kp, N, p);

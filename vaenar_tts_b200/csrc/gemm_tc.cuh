@@ -32,6 +32,12 @@ enum EpiMode : int {
   EPI_POSTERIOR = 4, // [logvar_named | mu_named] -> z = eps*exp(.5*lv)+mu, per-row log q  (N == 256)
 };
 
+// Compile-time epilogue feature mask of EPI_PLAIN (F_RUNTIME = decide from the GemmParams pointers at run time)
+enum : uint32_t {
+  F_BIAS = 1, F_RELU = 2, F_TANH = 4, F_BN = 8, F_TABLE = 16, F_RES = 32, F_OUT_F32 = 64, F_OUT_H = 128, F_OUT_LO = 256,
+  F_RUNTIME = 0x80000000u
+};
+
 struct GemmParams {
   // ---- tiling
   int batches;           // A-map batch extent (1 for flat row tiling)
@@ -43,6 +49,7 @@ struct GemmParams {
   int seg_shift[kMaxSegs];
   int seg_kblocks[kMaxSegs];
   int alg_k;             // algorithmic K (host-side accounting only)
+  unsigned long long* dbg;   // optional per-CTA phase timestamps (tuning aid), 8 x u64 per CTA
   int ln_cluster;        // EPI_LN: N is split over a 2-CTA cluster (blockIdx.y = rank), stats exchanged via DSMEM
   // ---- sequence geometry of the flattened rows (row = b * seq_T + t)
   int seq_T;
@@ -101,14 +108,13 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 // optional in-kernel phase timestamps (debug / tuning only): 8 x u64 per CTA, globaltimer ns
-__device__ unsigned long long* g_gemm_dbg = nullptr;
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE, uint32_t FEAT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
@@ -125,7 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* xbar = bars + 2 * Cfg::kStages + 2;             // [2] cluster LayerNorm exchange
   float* xred = reinterpret_cast<float*>(bars + 2 * Cfg::kStages + 4);   // [2][128] written by the peer CTA
 
-  unsigned long long* dbg = g_gemm_dbg ? g_gemm_dbg + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+  unsigned long long* dbg = p.dbg ? p.dbg + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
   if (dbg && threadIdx.x == 64) dbg[0] = gtime();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -222,9 +228,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const long grow0 = static_cast<long>(tile_b) * p.rows + tile_t0 + quad * 32;   // first row of this warp
     const int rows_here = min(32, p.rows - (tile_t0 + quad * 32));                  // valid rows of this warp (may be <= 0)
 
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    if (dbg && threadIdx.x == 64) dbg[2] = gtime();
     uint32_t v[32], w[32];
 
     // Warp-private staging slabs (the pipeline stages are idle now): 32 rows x 128 B, 16-byte chunks
@@ -237,7 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint8_t* s_f32 = slab;
     uint8_t* s_h = slab + 2 * 4096;
     uint8_t* s_lo = slab + 3 * 4096;
-    float* red = reinterpret_cast<float*>(smem_a + 8 * 4 * 4096);   // [2][128] LayerNorm partial exchange
+    float* red = reinterpret_cast<float*>(smem_a + 8 * 4 * 4096);   // [4][128] row-statistic exchange between column halves
     auto epi_bar = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     auto sw = [&](uint8_t* base, int row, int chunk) -> uint4* {
       return reinterpret_cast<uint4*>(base + row * 128 + ((chunk ^ (row & 7)) << 4));
@@ -270,20 +273,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     };
 
-    if (p.mode == EPI_PLAIN || p.mode == EPI_QKV) {
+    // LayerNorm: fetch this warp's first residual chunk into registers while the mainloop is still running
+    uint4 pre[16];
+    if constexpr (MODE == EPI_LN) {
+      const int n0p = n_tile * BLOCK_N + half * 64;
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int row = (it & 7) * 4 + (lane >> 3), chunk = lane & 7;
+        pre[it] = make_uint4(0u, 0u, 0u, 0u);
+        if (row < rows_here)
+          pre[it] = __ldg(reinterpret_cast<const uint4*>(p.residual + (grow0 + row) * p.res_ld + n0p + (it >> 3) * 32 + chunk * 4));
+      }
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    if (dbg && threadIdx.x == 64) dbg[2] = gtime();
+
+    if constexpr (MODE == EPI_PLAIN || MODE == EPI_QKV) {
+      constexpr bool RT = (FEAT & F_RUNTIME) != 0;
+      const bool f_bias = RT ? (p.bias != nullptr) : ((FEAT & F_BIAS) != 0);
+      const bool f_bn = RT ? (p.ch_scale != nullptr) : ((FEAT & F_BN) != 0);
+      const bool f_table = RT ? (p.add_table != nullptr) : ((FEAT & F_TABLE) != 0);
+      const bool f_res = RT ? (p.residual != nullptr) : ((FEAT & F_RES) != 0);
+      const bool f_f32 = RT ? (p.out_f32 != nullptr) : ((FEAT & F_OUT_F32) != 0);
+      const bool f_h = RT ? (p.out_h != nullptr) : ((FEAT & F_OUT_H) != 0);
+      const bool f_lo = RT ? (p.out_lo != nullptr) : ((FEAT & F_OUT_LO) != 0);
+      const int act = RT ? p.act : ((FEAT & F_RELU) ? 1 : ((FEAT & F_TANH) ? 2 : 0));
       for (int dc = half; dc < BLOCK_N / 64; dc += 2) {
         const int n0 = n_tile * BLOCK_N + dc * 64;
         if (n0 >= p.N) break;
         const int nvalid = min(64, p.N - n0);
         __syncwarp();
-        if (p.residual) {
+        if (f_res) {
           load_f32_slab(s_res, p.residual, p.res_ld, n0, nvalid);
           load_f32_slab(s_res + 4096, p.residual, p.res_ld, n0 + 32, nvalid - 32);
         }
         tmem_ld32(taddr + dc * 64, v);
         tmem_ld32(taddr + dc * 64 + 32, w);
         tmem_wait_ld();
-        if (p.mode == EPI_QKV && n0 >= p.n_rowmajor) {
+        if (MODE == EPI_QKV && n0 >= p.n_rowmajor) {
           // V^T store: [blk][b][h][64][vt_ld]; thread == row == consecutive t -> already coalesced
           if (row_ok) {
             const int nv = n0 - p.n_rowmajor;
@@ -300,8 +328,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           continue;
         }
         __syncwarp();   // residual slab visible
-        const float tscale = p.add_table ? __ldg(p.add_scale) : 0.f;
-        const float* trow = p.add_table ? p.add_table + static_cast<long>(st) * p.add_ld + n0 : nullptr;
+        const float tscale = f_table ? __ldg(p.add_scale) : 0.f;
+        const float* trow = f_table ? p.add_table + static_cast<long>(st) * p.add_ld + n0 : nullptr;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {          // the two 32-column halves of this 64-column chunk
           uint32_t* acc = hh ? w : v;
@@ -312,34 +340,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(acc[g * 4 + e]);
             if (nb + g * 4 < p.N) {
-              if (p.bias) {
+              if (f_bias) {
                 const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + nb + g * 4));
                 x[0] += bq.x; x[1] += bq.y; x[2] += bq.z; x[3] += bq.w;
               }
 #pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] = apply_act(x[e], p.act);
-              if (p.ch_scale) {
+              for (int e = 0; e < 4; ++e) x[e] = apply_act(x[e], act);
+              if (f_bn) {
                 const float4 sq = __ldg(reinterpret_cast<const float4*>(p.ch_scale + nb + g * 4));
                 const float4 hq = __ldg(reinterpret_cast<const float4*>(p.ch_shift + nb + g * 4));
                 x[0] = x[0] * sq.x + hq.x; x[1] = x[1] * sq.y + hq.y; x[2] = x[2] * sq.z + hq.z; x[3] = x[3] * sq.w + hq.w;
               }
-              if (p.add_table && row_ok) {
+              if (f_table && row_ok) {
                 const float4 tq = __ldg(reinterpret_cast<const float4*>(trow + hh * 32 + g * 4));
                 x[0] += tscale * tq.x; x[1] += tscale * tq.y; x[2] += tscale * tq.z; x[3] += tscale * tq.w;
               }
-              if (p.residual) {
+              if (f_res) {
                 const uint4 rq = *sw(s_res + hh * 4096, lane, g);
                 x[0] += __uint_as_float(rq.x); x[1] += __uint_as_float(rq.y);
                 x[2] += __uint_as_float(rq.z); x[3] += __uint_as_float(rq.w);
               }
             }
-            if (p.out_f32)
+            if (f_f32)
               *sw(s_f32 + hh * 4096, lane, g) = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]),
                                                             __float_as_uint(x[2]), __float_as_uint(x[3]));
             acc[g * 4 + 0] = __float_as_uint(x[0]); acc[g * 4 + 1] = __float_as_uint(x[1]);
             acc[g * 4 + 2] = __float_as_uint(x[2]); acc[g * 4 + 3] = __float_as_uint(x[3]);
           }
-          if (p.out_h) {
+          if (f_h) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {         // 8 columns -> one 16-byte fp16 chunk
               float f[8];
@@ -349,7 +377,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               u.x = pack_half2(f[0], f[1]); u.y = pack_half2(f[2], f[3]);
               u.z = pack_half2(f[4], f[5]); u.w = pack_half2(f[6], f[7]);
               *sw(s_h, lane, hh * 4 + g) = u;
-              if (p.out_lo) {
+              if (f_lo) {
                 float d[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) d[e] = f[e] - __half2float(__float2half_rn(f[e]));
@@ -362,25 +390,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
         __syncwarp();
-        if (p.out_f32) {
+        if (f_f32) {
           store_f32_slab(s_f32, p.out_f32, p.ld_f32, n0, nvalid);
           store_f32_slab(s_f32 + 4096, p.out_f32, p.ld_f32, n0 + 32, nvalid - 32);
         }
-        if (p.out_h) {
+        if (f_h) {
           store_f16_slab(s_h, p.out_h, p.ld_h, n0, nvalid);
-          if (p.out_lo) store_f16_slab(s_lo, p.out_lo, p.ld_h, n0, nvalid);
+          if (f_lo) store_f16_slab(s_lo, p.out_lo, p.ld_h, n0, nvalid);
         }
       }
-    } else if (p.mode == EPI_LN) {
-      // pass A: x = acc + bias + residual, row sums, x written back to TMEM
-      float sum = 0.f;
+    } else if constexpr (MODE == EPI_LN) {
+      // pass A: x = acc + bias + residual; row sum and sum of squares in one sweep; x written back to TMEM
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f}, sq4[4] = {0.f, 0.f, 0.f, 0.f};
       const int nbase = n_tile * BLOCK_N;            // column offset of this CTA (cluster split of N)
       const float inv_n = 1.f / static_cast<float>(p.ln_cluster ? 2 * BLOCK_N : BLOCK_N);
       const uint32_t peer = cluster_ctarank() ^ 1u;
       for (int dc = half; dc < BLOCK_N / 64; dc += 2) {
         const int n0 = nbase + dc * 64;
         __syncwarp();
-        if (p.residual) {
+        if (dc == half) {
+#pragma unroll
+          for (int it = 0; it < 16; ++it)
+            *sw(s_res + (it >> 3) * 4096, (it & 7) * 4 + (lane >> 3), lane & 7) = pre[it];
+        } else {
           load_f32_slab(s_res, p.residual, p.res_ld, n0, 64);
           load_f32_slab(s_res + 4096, p.residual, p.res_ld, n0 + 32, 32);
         }
@@ -393,70 +425,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           uint32_t* acc = hh ? w : v;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            float x[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(acc[g * 4 + e]);
-            if (p.bias) {
-              const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + hh * 32 + g * 4));
-              x[0] += bq.x; x[1] += bq.y; x[2] += bq.z; x[3] += bq.w;
-            }
-            if (p.residual) {
-              const uint4 rq = *sw(s_res + hh * 4096, lane, g);
-              x[0] += __uint_as_float(rq.x); x[1] += __uint_as_float(rq.y);
-              x[2] += __uint_as_float(rq.z); x[3] += __uint_as_float(rq.w);
-            }
-            sum += (x[0] + x[1]) + (x[2] + x[3]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[g * 4 + e] = __float_as_uint(x[e]);
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + hh * 32 + g * 4));
+            const uint4 rq = *sw(s_res + hh * 4096, lane, g);
+            const float x0 = __uint_as_float(acc[g * 4 + 0]) + bq.x + __uint_as_float(rq.x);
+            const float x1 = __uint_as_float(acc[g * 4 + 1]) + bq.y + __uint_as_float(rq.y);
+            const float x2 = __uint_as_float(acc[g * 4 + 2]) + bq.z + __uint_as_float(rq.z);
+            const float x3 = __uint_as_float(acc[g * 4 + 3]) + bq.w + __uint_as_float(rq.w);
+            sum4[0] += x0; sum4[1] += x1; sum4[2] += x2; sum4[3] += x3;
+            sq4[0] = fmaf(x0, x0, sq4[0]); sq4[1] = fmaf(x1, x1, sq4[1]);
+            sq4[2] = fmaf(x2, x2, sq4[2]); sq4[3] = fmaf(x3, x3, sq4[3]);
+            acc[g * 4 + 0] = __float_as_uint(x0); acc[g * 4 + 1] = __float_as_uint(x1);
+            acc[g * 4 + 2] = __float_as_uint(x2); acc[g * 4 + 3] = __float_as_uint(x3);
           }
         }
         tmem_st32(taddr + dc * 64, v);
         tmem_st32(taddr + dc * 64 + 32, w);
       }
       tmem_wait_st();
-      red[half * 128 + r] = sum;                     // combine the two column halves of every row
-      tc_fence_before();
+      float tot = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      float tsq = (sq4[0] + sq4[1]) + (sq4[2] + sq4[3]);
+      red[half * 128 + r] = tot;                     // combine the two column halves of every row
+      red[256 + half * 128 + r] = tsq;
       epi_bar();
-      tc_fence_after();
-      float tot = sum + red[(half ^ 1) * 128 + r];
-      if (p.ln_cluster) {                            // push this CTA's row sums into the peer, wait for the peer's
+      tot += red[(half ^ 1) * 128 + r];
+      tsq += red[256 + (half ^ 1) * 128 + r];
+      if (p.ln_cluster) {                            // push this CTA's row statistics into the peer, wait for the peer's
         if (half == 0) {
           st_cluster_f32(map_to_cta(smem_u32(&xred[r]), peer), tot);
+          st_cluster_f32(map_to_cta(smem_u32(&xred[128 + r]), peer), tsq);
           mbar_arrive_cluster(map_to_cta(smem_u32(&xbar[0]), peer));
         }
         mbar_wait_cluster(&xbar[0], 0);
         tot += xred[r];
+        tsq += xred[128 + r];
       }
       const float mean = tot * inv_n;
-      // pass B: centred second moment (TMEM reads only), this warp's chunks
-      float sq4[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int c = 2 * half; c < BLOCK_N / 32; c += 4) {
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-        __syncwarp();
-        tmem_ld32(taddr + (c + cc) * 32, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float d = __uint_as_float(v[j]) - mean;
-          sq4[j & 3] = fmaf(d, d, sq4[j & 3]);
-        }
-        }
-      }
-      const float sq_part = (sq4[0] + sq4[1]) + (sq4[2] + sq4[3]);
-      epi_bar();                                     // everyone has consumed the first exchange
-      red[half * 128 + r] = sq_part;
-      epi_bar();
-      float sqt = sq_part + red[(half ^ 1) * 128 + r];
-      if (p.ln_cluster) {
-        if (half == 0) {
-          st_cluster_f32(map_to_cta(smem_u32(&xred[128 + r]), peer), sqt);
-          mbar_arrive_cluster(map_to_cta(smem_u32(&xbar[1]), peer));
-        }
-        mbar_wait_cluster(&xbar[1], 0);
-        sqt += xred[128 + r];
-      }
-      const float rstd = 1.f / sqrtf(sqt * inv_n + p.ln_eps);
+      const float rstd = rsqrtf(fmaxf(tsq * inv_n - mean * mean, 0.f) + p.ln_eps);
       // pass C: normalise, gamma/beta, stage, coalesced copy-out
       for (int dc = half; dc < BLOCK_N / 64; dc += 2) {
         const int n0 = nbase + dc * 64;
@@ -476,13 +480,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             y[1] = (__uint_as_float(acc[g * 4 + 1]) - mean) * rstd * gq.y + bq.y;
             y[2] = (__uint_as_float(acc[g * 4 + 2]) - mean) * rstd * gq.z + bq.z;
             y[3] = (__uint_as_float(acc[g * 4 + 3]) - mean) * rstd * gq.w + bq.w;
-            if (p.out_f32)
-              *sw(s_f32 + hh * 4096, lane, g) = make_uint4(__float_as_uint(y[0]), __float_as_uint(y[1]),
+            *sw(s_f32 + hh * 4096, lane, g) = make_uint4(__float_as_uint(y[0]), __float_as_uint(y[1]),
                                                             __float_as_uint(y[2]), __float_as_uint(y[3]));
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[g * 4 + e] = __float_as_uint(y[e]);
           }
-          if (p.out_h) {
+          {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint4 u;
@@ -495,13 +498,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
         __syncwarp();
-        if (p.out_f32) {
-          store_f32_slab(s_f32, p.out_f32, p.ld_f32, n0, 64);
-          store_f32_slab(s_f32 + 4096, p.out_f32, p.ld_f32, n0 + 32, 32);
-        }
-        if (p.out_h) store_f16_slab(s_h, p.out_h, p.ld_h, n0, 64);
+        store_f32_slab(s_f32, p.out_f32, p.ld_f32, n0, 64);
+        store_f32_slab(s_f32 + 4096, p.out_f32, p.ld_f32, n0 + 32, 32);
+        store_f16_slab(s_h, p.out_h, p.ld_h, n0, 64);
       }
-    } else if (p.mode == EPI_COUPLING) {
+    } else if constexpr (MODE == EPI_COUPLING) {
       // columns [0, hN) = log_scale, [hN, 2 hN) = shift, hN = N / 2 = 64 (modules/flow.py:223-257).
       // Each warp half owns 32 of the 64 transformed channels; z is staged through the swizzled slabs.
       const int hN = p.N >> 1;
@@ -527,9 +528,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int e = 0; e < 4; ++e) {
           const float ls = __uint_as_float(v[g * 4 + e]) + lsb[e];
           const float sh = __uint_as_float(w[g * 4 + e]) + shb[e];
-          const float scale = 1.f / (1.f + expf(-(ls + 2.0f)));
-          o[e] = p.backward ? (zp[e] - sh) / (scale + 1e-12f) : scale * zp[e] + sh;
-          ld4[e] += logf(scale);
+          const float scale = __fdividef(1.f, 1.f + __expf(-(ls + 2.0f)));   // sigmoid(ls + 2), flow.py:231
+          o[e] = p.backward ? __fdividef(zp[e] - sh, scale + 1e-12f) : scale * zp[e] + sh;
+          ld4[e] += __logf(scale);
           v[g * 4 + e] = __float_as_uint(o[e]);
         }
         *sw(s_f32, lane, g) = make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]),
@@ -554,7 +555,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const float tot = logdet + red[128 + r];
         p.row_acc[grow] += in_len ? (p.backward ? -tot : tot) : 0.f;
       }
-    } else if (p.mode == EPI_POSTERIOR) {
+    } else if constexpr (MODE == EPI_POSTERIOR) {
       // modules/posterior.py:20-72 with the models.py:136 name swap already applied by the packing order:
       // columns [0, L) = log-variance (mu_projection), [L, 2L) = mean (logvar_projection), L = N / 2.
       const int L = p.N >> 1;
