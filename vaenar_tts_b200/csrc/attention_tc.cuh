@@ -16,8 +16,8 @@
 //           A-operand layout), O += P V accumulated in TMEM; ctx = O / l.
 // No online rescaling of O is ever needed, the whole row never has to be resident, and Tk is unbounded.
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 softmax: two warps per TMEM lane
-// quadrant, each owning one 64-key panel of every 128-key block (row statistics combined through shared memory).
+// Warp roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..17 softmax: four warps per TMEM lane
+// quadrant, each owning 32 keys of every 128-key block (row statistics combined through shared memory).
 // Key blocks that cannot contribute to a LIVE row are skipped (above the causal diagonal, beyond key_len).  Fully
 // masked rows attend uniformly to all T_k keys, i.e. their context is the column mean of V: tiles that contain such
 // rows compute that mean once from V^T (fp32) and write it directly, so dead rows / dead tiles cost no MMA work.
@@ -26,8 +26,9 @@
 
 namespace vb {
 
-constexpr int ATT_THREADS = 320;
-constexpr int ATT_SOFTMAX_THREADS = 256;
+constexpr int ATT_GROUPS = 4;                       // column groups (warps per TMEM lane quadrant)
+constexpr int ATT_SOFTMAX_THREADS = 128 * ATT_GROUPS;
+constexpr int ATT_THREADS = 64 + ATT_SOFTMAX_THREADS;
 constexpr int ATT_BQ = 128;     // queries per CTA
 constexpr int ATT_BK = 128;     // keys per block
 constexpr int ATT_D = 64;       // head dim
@@ -35,7 +36,7 @@ constexpr int ATT_QBYTES = ATT_BQ * ATT_D * 2;       // 16 KB
 constexpr int ATT_KBYTES = ATT_BK * ATT_D * 2;       // 16 KB
 constexpr int ATT_VBYTES = ATT_D * ATT_BK * 2;       // 16 KB (two 64-key panels of 8 KB)
 constexpr int ATT_PBYTES = ATT_BQ * ATT_BK * 2;      // 32 KB (two 64-key panels of 16 KB)
-constexpr int ATT_SMEM = ATT_QBYTES + 2 * ATT_KBYTES + 2 * ATT_VBYTES + 2 * ATT_PBYTES + 256 + 3 * 2 * ATT_BQ * 4 + 256 + 1024;
+constexpr int ATT_SMEM = ATT_QBYTES + 2 * ATT_KBYTES + 2 * ATT_VBYTES + 2 * ATT_PBYTES + 256 + 3 * ATT_GROUPS * ATT_BQ * 4 + 256 + 1024;
 
 struct AttnParams {
   int B, H, Tq, Tk;
@@ -93,7 +94,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     nblk = min((p.Tk + ATT_BK - 1) / ATT_BK, (klen + ATT_BK - 1) / ATT_BK);
     if (p.causal) nblk = min(nblk, (min(q_hi, qlen) - 1) / ATT_BK + 1);
   }
-  float* vmean = red + 6 * ATT_BQ;   // [64] column mean of V for fully masked rows
+  float* vmean = red + 3 * ATT_GROUPS * ATT_BQ;   // [64] column mean of V for fully masked rows
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -189,7 +190,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else {
     // ===================== softmax / epilogue warps =====================
     const int quad = warp & 3;                   // TMEM lane quadrant (hardware rule: warp_id % 4)
-    const int half = (warp - 2) >> 2;            // which 64-key panel of each 128-key block this warp owns
+    const int grp = (warp - 2) >> 2;             // which 32 keys of each 128-key block this warp owns
     const int r = quad * 32 + lane;
     const int q = q0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
@@ -198,15 +199,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const float sl2 = p.scale * 1.4426950408889634f;       // scale * log2(e)
     const float inv_tk = 1.0f / static_cast<float>(p.Tk);
     uint32_t v[32];
-    auto softmax_bar = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    auto softmax_bar = []() { asm volatile("bar.sync 1, %0;" ::"n"(ATT_SOFTMAX_THREADS) : "memory"); };
+    float* red_m = red;                              // [G][128]
+    float* red_l = red + ATT_GROUPS * ATT_BQ;        // [G][128]
+    float* red_s = red + 2 * ATT_GROUPS * ATT_BQ;    // [G][128]
 
     if (has_dead_rows) {
       // column mean of V over ALL Tk padded keys (the uniform distribution of attention.py:240-242), fp32
-      const int sidx = (warp - 2) * 32 + lane;      // 0..255: 4 threads per head channel
-      const int d = sidx >> 2, part = sidx & 3;
+      const int sidx = (warp - 2) * 32 + lane;      // 0..511: 8 threads per head channel
+      const int d = sidx >> 3, part = sidx & 7;
       const __half* vrow = p.vt + (p.vt_row0 + (static_cast<long>(b) * p.H + h) * ATT_D + d) * p.vt_ld;
       float acc = 0.f;
-      for (int t0 = part * 8; t0 < p.Tk; t0 += 32) {
+      for (int t0 = part * 8; t0 < p.Tk; t0 += 64) {
         if (t0 + 8 <= p.Tk) {
           const uint4 u = *reinterpret_cast<const uint4*>(vrow + t0);
           const __half2* hp = reinterpret_cast<const __half2*>(&u);
@@ -221,6 +225,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
       if (part == 0) vmean[d] = acc * inv_tk;
     }
 
@@ -231,48 +236,53 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int st = i & 1;
       mbar_wait(&s_full[st], (i >> 1) & 1);
       tc_fence_after();
+      __syncwarp();
+      tmem_ld32(tmem_S + st * ATT_BK + lane_off + grp * 32, v);
+      tmem_wait_ld();
+      const int kk0 = i * ATT_BK + grp * 32;
+      float bm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        __syncwarp();
-        tmem_ld32(tmem_S + st * ATT_BK + lane_off + half * 64 + c * 32, v);
-        tmem_wait_ld();
-        const int kk0 = i * ATT_BK + half * 64 + c * 32;
-        float bm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      for (int e = 0; e < 32; ++e) {
+        const int kk = kk0 + e;
+        const bool ok = (kk < klen) && (!p.causal || kk <= q);
+        const float sv = ok ? __uint_as_float(v[e]) : -INFINITY;
+        bm[e & 3] = fmaxf(bm[e & 3], sv);
+        if (kWriteAli) v[e] = __float_as_uint(sv);
+      }
+      const float cm = fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3]));
+      if (kWriteAli) {
+        const float mn = fmaxf(m, cm);
+        if (mn > -INFINITY) {
+          float add[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int kk = kk0 + e;
-          const bool ok = (kk < klen) && (!p.causal || kk <= q);
-          const float sv = ok ? __uint_as_float(v[e]) : -INFINITY;
-          bm[e & 3] = fmaxf(bm[e & 3], sv);
-          if (kWriteAli) v[e] = __float_as_uint(sv);
+          for (int e = 0; e < 32; ++e) add[e & 3] += ex2_approx((__uint_as_float(v[e]) - mn) * sl2);
+          l = l * ex2_approx((m - mn) * sl2) + (add[0] + add[1]) + (add[2] + add[3]);
+          m = mn;
         }
-        const float cm = fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3]));
-        if (kWriteAli) {
-          const float mn = fmaxf(m, cm);
-          if (mn > -INFINITY) {
-            float add[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int e = 0; e < 32; ++e) add[e & 3] += ex2_approx((__uint_as_float(v[e]) - mn) * sl2);
-            l = l * ex2_approx((m - mn) * sl2) + (add[0] + add[1]) + (add[2] + add[3]);
-            m = mn;
-          }
-        } else {
-          m = fmaxf(m, cm);
-        }
+      } else {
+        m = fmaxf(m, cm);
       }
       tc_fence_before();
       mbar_arrive(&s_empty[st]);
     }
-    // combine the two column halves of every row
-    red[half * ATT_BQ + r] = m;
-    if (kWriteAli) red[2 * ATT_BQ + half * ATT_BQ + r] = l;
+    // combine the column groups of every row
+    red_m[grp * ATT_BQ + r] = m;
+    if (kWriteAli) red_l[grp * ATT_BQ + r] = l;
     softmax_bar();
     {
-      const float mo = red[(half ^ 1) * ATT_BQ + r];
-      const float mn = fmaxf(m, mo);
+      float mn = m;
+#pragma unroll
+      for (int g = 0; g < ATT_GROUPS; ++g) mn = fmaxf(mn, red_m[g * ATT_BQ + r]);
       if (kWriteAli) {
-        const float lo = red[2 * ATT_BQ + (half ^ 1) * ATT_BQ + r];
-        l = (mn > -INFINITY) ? l * ex2_approx((m - mn) * sl2) + lo * ex2_approx((mo - mn) * sl2) : 0.f;
+        float lt = 0.f;
+        if (mn > -INFINITY) {
+#pragma unroll
+          for (int g = 0; g < ATT_GROUPS; ++g) {
+            const float mg = red_m[g * ATT_BQ + r];
+            if (mg > -INFINITY) lt += red_l[g * ATT_BQ + r] * ex2_approx((mg - mn) * sl2);
+          }
+        }
+        l = lt;
       }
       m = mn;
     }
@@ -289,44 +299,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(&s_full[st], (i >> 1) & 1);
       mbar_wait(&p_empty[sp], ((iv >> 1) & 1) ^ 1);
       tc_fence_after();
-      // this warp's 64-key panel of the P tile: 128 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7)
-      uint8_t* prow = sP + sp * ATT_PBYTES + half * (ATT_PBYTES / 2) + r * 128;
+      // this warp's 32 keys inside the 64-key panel (grp >> 1): 128 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7)
+      uint8_t* prow = sP + sp * ATT_PBYTES + (grp >> 1) * (ATT_PBYTES / 2) + r * 128;
+      __syncwarp();
+      tmem_ld32(tmem_S + st * ATT_BK + lane_off + grp * 32, v);
+      tmem_wait_ld();
+      const int kk0 = iv * ATT_BK + grp * 32;
+      float pr[32];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        __syncwarp();
-        tmem_ld32(tmem_S + st * ATT_BK + lane_off + half * 64 + c * 32, v);
-        tmem_wait_ld();
-        const int kk0 = iv * ATT_BK + half * 64 + c * 32;
-        float pr[32];
+      for (int e = 0; e < 32; ++e) {
+        const int kk = kk0 + e;
+        float pe;
+        if (row_dead) {
+          pe = 0.f;                 // dead rows take the V column mean directly (epilogue)
+        } else {
+          const bool ok = (kk < klen) && (!p.causal || kk <= q);
+          pe = ok ? ex2_approx(__uint_as_float(v[e]) * sl2 - msl2) : 0.f;
+        }
+        ls[e & 3] += pe;
+        pr[e] = pe * inv_l;           // normalised already when kWriteAli (inv_l == 1 otherwise)
+      }
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int kk = kk0 + e;
-          float pe;
-          if (row_dead) {
-            pe = 0.f;                 // dead rows take the V column mean directly (epilogue)
-          } else {
-            const bool ok = (kk < klen) && (!p.causal || kk <= q);
-            pe = ok ? ex2_approx(__uint_as_float(v[e]) * sl2 - msl2) : 0.f;
-          }
-          ls[e & 3] += pe;
-          pr[e] = pe * inv_l;           // normalised already when kWriteAli (inv_l == 1 otherwise)
-          if (kWriteAli && row_dead) pr[e] = (kk < p.Tk) ? inv_tk : 0.f;   // alignments of a dead row: uniform
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = c * 4 + g;
-          uint4 u;
-          u.x = pack_half2(pr[g * 8 + 0], pr[g * 8 + 1]);
-          u.y = pack_half2(pr[g * 8 + 2], pr[g * 8 + 3]);
-          u.z = pack_half2(pr[g * 8 + 4], pr[g * 8 + 5]);
-          u.w = pack_half2(pr[g * 8 + 6], pr[g * 8 + 7]);
-          if (row_dead) u = make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = u;
-        }
-        if (kWriteAli && row_store) {
-          float* arow = p.ali + ((static_cast<long>(b) * p.H + h) * p.Tq + q) * p.Tk + kk0;
-          for (int e = 0; e < 32 && kk0 + e < p.Tk; ++e) arow[e] = pr[e];
-        }
+      for (int g = 0; g < 4; ++g) {
+        const int chunk = (grp & 1) * 4 + g;
+        uint4 u;
+        u.x = pack_half2(pr[g * 8 + 0], pr[g * 8 + 1]);
+        u.y = pack_half2(pr[g * 8 + 2], pr[g * 8 + 3]);
+        u.z = pack_half2(pr[g * 8 + 4], pr[g * 8 + 5]);
+        u.w = pack_half2(pr[g * 8 + 6], pr[g * 8 + 7]);
+        *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = u;
+      }
+      if (kWriteAli && row_store) {
+        float* arow = p.ali + ((static_cast<long>(b) * p.H + h) * p.Tq + q) * p.Tk + kk0;
+        for (int e = 0; e < 32 && kk0 + e < p.Tk; ++e) arow[e] = row_dead ? inv_tk : pr[e];
       }
       fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
@@ -338,36 +343,40 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int k_done = nblk * ATT_BK;
       float* arow = p.ali + ((static_cast<long>(b) * p.H + h) * p.Tq + q) * p.Tk;
       const float fill = row_dead ? inv_tk : 0.f;
-      for (int kk = k_done + half; kk < p.Tk; kk += 2) arow[kk] = fill;
+      for (int kk = k_done + grp; kk < p.Tk; kk += ATT_GROUPS) arow[kk] = fill;
     }
 
-    // ---- epilogue: ctx = O / l ; each half handles 32 of the 64 head channels
+    // ---- epilogue: ctx = O / l ; column groups 0 and 1 each write 32 of the 64 head channels
     float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
-    red[4 * ATT_BQ + half * ATT_BQ + r] = lsum;
+    red_s[grp * ATT_BQ + r] = lsum;
     softmax_bar();
-    lsum += red[4 * ATT_BQ + (half ^ 1) * ATT_BQ + r];
-    if (nblk > 0) {
-      mbar_wait(o_full, 0);
-      tc_fence_after();
-      __syncwarp();
-      tmem_ld32(tmem_O + lane_off + half * 32, v);
-      tmem_wait_ld();
-    }
-    const float on = row_dead ? 0.f : (kWriteAli ? 1.0f : 1.0f / lsum);
-    if (row_store) {
-      __half* dst = p.ctx + (static_cast<long>(b) * p.Tq + q) * p.ctx_ld + h * ATT_D + half * 32;
+    if (grp < 2) {
+      lsum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float f[8];
+      for (int g = 0; g < ATT_GROUPS; ++g) lsum += red_s[g * ATT_BQ + r];
+      if (nblk > 0) {
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        __syncwarp();
+        tmem_ld32(tmem_O + lane_off + grp * 32, v);
+        tmem_wait_ld();
+      }
+      const float on = row_dead ? 0.f : (kWriteAli ? 1.0f : 1.0f / lsum);
+      if (row_store) {
+        __half* dst = p.ctx + (static_cast<long>(b) * p.Tq + q) * p.ctx_ld + h * ATT_D + grp * 32;
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          f[e] = row_dead ? vmean[half * 32 + j + e] : __uint_as_float(v[j + e]) * on;
-        uint4 u;
-        u.x = pack_half2(f[0], f[1]);
-        u.y = pack_half2(f[2], f[3]);
-        u.z = pack_half2(f[4], f[5]);
-        u.w = pack_half2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(dst + j) = u;
+        for (int j = 0; j < 32; j += 8) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            f[e] = row_dead ? vmean[grp * 32 + j + e] : __uint_as_float(v[j + e]) * on;
+          uint4 u;
+          u.x = pack_half2(f[0], f[1]);
+          u.y = pack_half2(f[2], f[3]);
+          u.z = pack_half2(f[4], f[5]);
+          u.w = pack_half2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(dst + j) = u;
+        }
       }
     }
     tc_fence_before();
