@@ -119,6 +119,8 @@ struct vaenar_model {
   std::vector<PackOp> host_ops;
   std::vector<const float*> host_ptrs;
   bool attrs_set = false;
+  cudaStream_t side_stream = nullptr;   // second launch chain for batch-split inference (fork/join with events)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   int add_param(const std::string& n, std::initializer_list<int64_t> dims, bool trainable = true) {
     ParamInfo p;
@@ -488,6 +490,8 @@ struct ProfileScope {
   X(128, EPI_PLAIN, F_BIAS | F_RELU | F_BN | F_OUT_H)                                                 \
   X(128, EPI_PLAIN, F_BIAS | F_TANH | F_BN | F_OUT_H | F_OUT_LO)                                      \
   X(128, EPI_PLAIN, F_BIAS | F_BN | F_OUT_H | F_OUT_LO)                                               \
+  X(256, EPI_PLAIN, F_BIAS | F_TANH | F_BN | F_OUT_H | F_OUT_LO)                                      \
+  X(256, EPI_PLAIN, F_BIAS | F_BN | F_OUT_H | F_OUT_LO)                                               \
   X(128, EPI_PLAIN, F_BIAS | F_OUT_F32 | F_OUT_H)                                                     \
   X(128, EPI_PLAIN, F_BIAS | F_RELU | F_TABLE | F_OUT_F32 | F_OUT_H)                                  \
   X(128, EPI_PLAIN, F_BIAS | F_OUT_F32 | F_OUT_H | F_OUT_LO)                                          \
@@ -1049,7 +1053,7 @@ static void posterior_fwd(Ctx& c, const float* mels, const float* text_embd, con
 
 // TransformerDecoder.call (modules/decoder.py:181-199), inference mode
 static void decoder_fwd(Ctx& c, const float* z, const float* text_embd, const int* z_len, const int* t_len, int B, int Tt,
-                        int Tz, int rf, float* initial, float* mel, float* ali) {
+                        int Tz, int rf, float* initial, float* mel, float* ali, int64_t ali_blk_stride = 0) {
   const vaenar_hparams_t& h = c.m->hp;
   const int d = h.dec_att_dim, H = h.dec_heads, F = h.dec_ffn, E = h.enc_hidden, L = h.latent_dim, O = h.out_dim,
             C = h.post_filters;
@@ -1080,7 +1084,7 @@ static void decoder_fwd(Ctx& c, const float* z, const float* text_embd, const in
   }
   for (int i = 0; i < h.dec_nblk; ++i)
     xblk_fwd(c, "dec.blk" + std::to_string(i), "decoder.attentions." + std::to_string(i), x, xb, B, Tz, d, H, F, z_len, kv, i,
-             Tt, t_len, ali ? ali + static_cast<int64_t>(i) * B * H * Tz * Tt : nullptr);
+             Tt, t_len, ali ? ali + static_cast<int64_t>(i) * (ali_blk_stride ? ali_blk_stride : static_cast<int64_t>(B) * H * Tz * Tt) : nullptr);
   {  // out_projection, first rf*80 columns only (decoder.py:193); [B*Tz, rf*80] == [B*Tz*rf, 80]
     GemmParams p = gp();
     p.mode = EPI_PLAIN; p.N = rf * O; segs_plain(p, d);
@@ -1097,7 +1101,7 @@ static void decoder_fwd(Ctx& c, const float* z, const float* text_embd, const in
     p.mode = EPI_PLAIN; p.N = C; p.act = (i < h.post_n_conv - 1) ? 2 : 0; segs_conv(p, h.post_kernel, cin, true);
     p.bias = c.P(pn + ".conv1d.bias"); p.ch_scale = c.V(pk + ".bn_scale"); p.ch_shift = c.V(pk + ".bn_shift");
     p.out_h = out_h; p.out_lo = out_l; p.ld_h = C;
-    run_gemm(c, 128, AOp{in_h, cin, cin}, AOp{in_l, cin, cin}, B, Tm, c.W(pk), c.WM(pk).K, C, p);
+    run_gemm(c, 256, AOp{in_h, cin, cin}, AOp{in_l, cin, cin}, B, Tm, c.W(pk), c.WM(pk).K, C, p);   // one wave: 112 CTAs
     in_h = out_h; in_l = out_l;
     out_h = (in_h == pa_h) ? pb_h : pa_h;
     out_l = (in_l == pa_l) ? pb_l : pa_l;
@@ -1160,14 +1164,58 @@ static void elbo_fwd(Ctx& c, const int* texts, const float* mels, const int* m_l
   c.ws_off = mark;
 }
 
-static void inference_fwd(Ctx& c, const int* texts, const int* t_len, const int* z_len, int B, int Tt, int Tz, int rf,
-                          float* z_io, float* text_embd, float* mel, float* ali, float* logp) {
+static void inference_one(Ctx& c, const int* texts, const int* t_len, const int* z_len, int B, int Tt, int Tz, int rf,
+                          float* z_io, float* text_embd, float* mel, float* ali, int64_t ali_blk_stride, float* logp) {
   const vaenar_hparams_t& h = c.m->hp;
   const int64_t mark = c.ws_off;
   float* ini = c.alloc<float>(static_cast<int64_t>(B) * Tz * rf * h.out_dim);
   encoder_fwd(c, texts, t_len, B, Tt, h.mel_text_len_ratio / static_cast<float>(rf), text_embd);
   prior_sample(c, text_embd, t_len, z_len, B, Tt, Tz, z_io, logp);
-  decoder_fwd(c, z_io, text_embd, z_len, t_len, B, Tt, Tz, rf, ini, mel, ali);
+  decoder_fwd(c, z_io, text_embd, z_len, t_len, B, Tt, Tz, rf, ini, mel, ali, ali_blk_stride);
+  c.ws_off = mark;
+}
+
+// VAENAR.inference.  Utterances are independent in inference (BatchNorm uses moving statistics), and most
+// kernels of the chain occupy well under 148 SMs, so the batch is split in two halves that run as two concurrent
+// launch chains (caller stream + an internal side stream, fork/join with events; capturable into one CUDA graph).
+static void inference_fwd(Ctx& c, const int* texts, const int* t_len, const int* z_len, int B, int Tt, int Tz, int rf,
+                          float* z_io, float* text_embd, float* mel, float* ali, float* logp) {
+  const vaenar_hparams_t& h = c.m->hp;
+  const int B0 = B >= 4 ? B / 2 : B, B1 = B - B0;
+  const int64_t ali_stride = static_cast<int64_t>(B) * h.dec_heads * Tz * Tt;
+  const int64_t mark = c.ws_off;
+  if (B1 == 0) {
+    inference_one(c, texts, t_len, z_len, B, Tt, Tz, rf, z_io, text_embd, mel, ali, ali_stride, logp);
+    return;
+  }
+  Ctx c1 = c;                      // second chain: its own workspace region and stream
+  if (!c.dry) {
+    vaenar_model* m = c.m;
+    if (!m->side_stream) {
+      VB_CUDA(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
+      VB_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+      VB_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    }
+    c1.stream = m->side_stream;
+    VB_CUDA(cudaEventRecord(m->ev_fork, c.stream));
+    VB_CUDA(cudaStreamWaitEvent(c1.stream, m->ev_fork, 0));
+  }
+  inference_one(c, texts, t_len, z_len, B0, Tt, Tz, rf, z_io, text_embd, mel, ali, ali_stride, logp);
+  // region of the second chain starts after the first chain's peak
+  c1.ws_off = align_up(c.ws_peak, 1024);
+  c1.ws_peak = c1.ws_off;
+  const int L = h.latent_dim, E = h.enc_hidden, O = h.out_dim;
+  inference_one(c1, c.dry ? nullptr : texts + static_cast<int64_t>(B0) * Tt, c.dry ? nullptr : t_len + B0,
+                c.dry ? nullptr : z_len + B0, B1, Tt, Tz, rf, c.dry ? nullptr : z_io + static_cast<int64_t>(B0) * Tz * L,
+                c.dry ? nullptr : text_embd + static_cast<int64_t>(B0) * Tt * E,
+                c.dry ? nullptr : mel + static_cast<int64_t>(B0) * Tz * rf * O,
+                (c.dry || !ali) ? nullptr : ali + static_cast<int64_t>(B0) * h.dec_heads * Tz * Tt, ali_stride,
+                c.dry ? nullptr : logp + B0);
+  c.ws_peak = std::max(c.ws_peak, c1.ws_peak);
+  if (!c.dry) {
+    VB_CUDA(cudaEventRecord(c.m->ev_join, c1.stream));
+    VB_CUDA(cudaStreamWaitEvent(c.stream, c.m->ev_join, 0));
+  }
   c.ws_off = mark;
 }
 
@@ -1288,6 +1336,11 @@ int vaenar_create(const vaenar_hparams_t* hps, vaenar_handle_t* out) {
   API_END
 }
 int vaenar_destroy(vaenar_handle_t h) {
+  if (h) {
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  }
   delete h;
   return 0;
 }
