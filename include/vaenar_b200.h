@@ -33,7 +33,19 @@ typedef struct vaenar_hparams {
   int32_t prior_n_blk, prior_n_tblk, prior_att_dim, prior_heads, prior_ffn;
   int32_t latent_dim, out_dim, max_reduction_factor, final_reduction_factor;
   float mel_text_len_ratio;
+  /* dropout rates (configs/hparams.py:299-300,321,326-327): encoder prenet / positional, posterior prenet / positional, postnet */
+  float enc_pre_drop_rate, enc_pos_drop_rate, posterior_pre_drop_rate, posterior_pos_drop_rate, post_drop_rate;
 } vaenar_hparams_t;
+
+/* Training-mode forward options.  Dropout keep-masks (values 0 or 1/(1-rate), fp32, shape of the tensor they multiply)
+ * are consumed in the reference's call order: encoder prenet conv 0..n-1, encoder positional, [posterior prenet 1, 2,
+ * posterior positional,] postnet conv 0..n-1.  masks == NULL: generated on device from (seed, site index). */
+typedef struct vaenar_train_opts {
+  int32_t n_masks;
+  const float* const* masks; /* HOST array of device pointers, or NULL */
+  uint64_t seed;
+  int32_t update_bn_stats;   /* apply the BatchNorm moving-average side effect (momentum 0.99) */
+} vaenar_train_opts_t;
 
 const char* vaenar_last_error(void);
 int vaenar_abi_version(void);
@@ -113,6 +125,24 @@ int vaenar_elbo_fwd(vaenar_handle_t h, const float* params, const void* packed, 
                     const int32_t* text_lengths, const int32_t* z_lengths, const float* eps, int B, int T_text,
                     int T_mel, int T_z, int rf, float* mel_out, float* l2, float* kl, float* length_loss,
                     float* alignments, void* stream);
+
+/* VAENAR.call forward with training=True semantics (models/models.py:105-197 as called by train.py:129-134):
+ * BatchNorm uses batch statistics over (batch, time) incl. padding and updates its moving averages in `params`,
+ * dropout is active (encoder, posterior prenet/positional, postnet).  Forward only: the backward pass is not part of
+ * this ABI yet. */
+int vaenar_elbo_fwd_train(vaenar_handle_t h, float* params, const void* packed, void* ws, int64_t ws_bytes,
+                          const int32_t* texts, const float* mels, const int32_t* mel_lengths,
+                          const int32_t* text_lengths, const int32_t* z_lengths, const float* eps, int B, int T_text,
+                          int T_mel, int T_z, int rf, const vaenar_train_opts_t* opts, float* mel_out, float* l2,
+                          float* kl, float* length_loss, float* alignments, void* stream);
+
+/* VAENAR.init (models/models.py:212-226): encoder(training=True) -> prior.init (data-dependent ActNorm
+ * initialisation, modules/prior.py:171-186, modules/flow.py:189-196, written into `params`) -> decoder at
+ * rf = max_reduction_factor.  z_io: N(0,1) noise in, latents out; mel [B, T_z*max_rf, 80].  The packed arena must be
+ * rebuilt (vaenar_pack_weights) afterwards. */
+int vaenar_init(vaenar_handle_t h, float* params, void* packed, void* ws, int64_t ws_bytes, const int32_t* texts,
+                const int32_t* text_lengths, const int32_t* z_lengths, int B, int T_text, int T_z,
+                const vaenar_train_opts_t* opts, float* z_io, float* mel, void* stream);
 
 /* N(0, stddev) noise from the counter-based generator (replaces tf.random.normal at
  * modules/posterior.py:35 and modules/prior.py:35). */

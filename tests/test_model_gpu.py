@@ -94,13 +94,62 @@ def test_golden_call_eval(case):
         assert float((v.cpu() - t(g, "eval_ali_" + k)).abs().max()) < 5e-3
 
 
-def test_training_mode_refused():
-    """No silent inference-mode arithmetic when training=True is requested."""
+def _masks(g, prefix):
+    return [t(g, f"{prefix}_dropout_{i:02d}") for i in range(int(g[f"{prefix}_n_dropout"]))]
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_golden_call_train_forward(case):
+    """VAENAR.call with training=True (train.py:129-134): dropout masks of the reference run injected, BatchNorm batch
+    statistics, and the moving-average side effect."""
+    ohps, g, P = load_case(case)
+    m = make_model(ohps, P)
+    mel, l2, kl, ll, _ = m(inputs=t(g, "texts"), mel_targets=t(g, "mels"), mel_lengths=t(g, "m_len"),
+                           text_lengths=t(g, "t_len"), reduction_factor=int(g["rf"]), training=True, reduce_loss=True,
+                           eps=t(g, "train_eps"), dropout_masks=_masks(g, "train"))
+    # batch-statistics BatchNorm + inverted dropout give random-weight mels of magnitude >1 (the 1e-3 tolerance is
+    # stated for [0,1]-normalised mels): scale the tolerance by the mean output magnitude.
+    # With the 60-row batches of the golden cases the batch statistics amplify operand rounding: the fp16-operand
+    # emulation of the ORACLE itself sits at 1.4-1.5e-3 of the output magnitude here, so the bound is 2e-3 relative.
+    scale = max(1.0, float(t(g, "train_mel").abs().mean()))
+    assert masked_mae(mel, t(g, "train_mel"), t(g, "m_len")) <= 2 * MEL_MAE_TOL * scale
+    assert rel(l2, g["train_l2"]) < REL_TOL and rel(kl, g["train_kl"]) < REL_TOL and rel(ll, g["train_len"]) < 1e-2
+    sd = m.state_dict()
+    for k in sd:
+        if k.endswith("moving_mean") or k.endswith("moving_variance"):
+            ref = t(g, "train_bnstat/" + k)
+            assert float((sd[k].cpu() - ref).abs().max()) < 2e-4 + 2e-3 * float(ref.abs().max()), k
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_golden_init(case):
+    """VAENAR.init (models/models.py:212-226): data-dependent ActNorm initialisation"""
+    ohps, g, P = load_case(case)
+    m = make_model(ohps, P)
+    mel = m.init(t(g, "texts"), t(g, "m_len"), t(g, "t_len"), epsilon=t(g, "init_epsilon"),
+                 dropout_masks=_masks(g, "init"))
+    ref = t(g, "init_mel")
+    assert mel.shape == ref.shape
+    assert float((mel.cpu() - ref).abs().mean()) <= 2e-3
+    sd = m.state_dict()
+    for k in sd:
+        if ".actnorm." in k:
+            r = t(g, "init_actnorm/" + k)
+            assert float((sd[k].cpu() - r).abs().max()) < 5e-3 * max(1.0, float(r.abs().max())), k
+    # the initialised model must still run (weights repacked)
+    mel2, _ = m.inference(t(g, "texts"), t(g, "m_len"), t(g, "t_len"), reduction_factor=2)
+    assert torch.isfinite(mel2).all()
+
+
+def test_training_forward_generated_masks_runs():
+    """Without injected masks the dropout masks come from the on-device Philox generator: finite, different from eval."""
     ohps, g, P = load_case(list(CASES)[0])
     m = make_model(ohps, P)
-    with pytest.raises(NotImplementedError):
-        m(inputs=t(g, "texts"), mel_targets=t(g, "mels"), mel_lengths=t(g, "m_len"), text_lengths=t(g, "t_len"),
-          reduction_factor=2, training=True, reduce_loss=True)
+    args = dict(inputs=t(g, "texts"), mel_targets=t(g, "mels"), mel_lengths=t(g, "m_len"), text_lengths=t(g, "t_len"),
+                reduction_factor=2, reduce_loss=True, eps=t(g, "eval_eps"))
+    a = m(training=True, update_bn_stats=False, **args)
+    b = m(training=False, **args)
+    assert torch.isfinite(a[0]).all() and float((a[0] - b[0]).abs().max()) > 1e-3
 
 
 @pytest.mark.parametrize("B,Tt,Tm", [(16, 148, 870)])

@@ -19,7 +19,13 @@ class HParamsStruct(ctypes.Structure):
         "dec_nblk", "dec_att_dim", "dec_heads", "dec_ffn", "post_n_conv", "post_filters", "post_kernel",
         "posterior_pre_hidden", "posterior_nblk", "posterior_att_dim", "posterior_heads", "posterior_ffn",
         "prior_n_blk", "prior_n_tblk", "prior_att_dim", "prior_heads", "prior_ffn",
-        "latent_dim", "out_dim", "max_reduction_factor", "final_reduction_factor")] + [("mel_text_len_ratio", c_float)]
+        "latent_dim", "out_dim", "max_reduction_factor", "final_reduction_factor")] + [(n, c_float) for n in (
+        "mel_text_len_ratio", "enc_pre_drop_rate", "enc_pos_drop_rate", "posterior_pre_drop_rate",
+        "posterior_pos_drop_rate", "post_drop_rate")]
+
+
+class TrainOpts(ctypes.Structure):
+    _fields_ = [("n_masks", c_int32), ("masks", POINTER(c_void_p)), ("seed", c_uint64), ("update_bn_stats", c_int32)]
 
 
 _P = c_void_p
@@ -49,6 +55,9 @@ _SIGS = {
                                  _P]),
     "vaenar_elbo_fwd": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P,
                                 _P, _P, _P, _P, _P]),
+    "vaenar_elbo_fwd_train": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                      POINTER(TrainOpts), _P, _P, _P, _P, _P, _P]),
+    "vaenar_init": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, POINTER(TrainOpts), _P, _P, _P]),
     "vaenar_randn": (c_int, [_P, c_int64, c_uint64, c_uint64, c_float, _P]),
     "vaenar_launch_count": (ctypes.c_long, []),
     "vaenar_profile_enable": (c_int, [c_int]),

@@ -418,6 +418,13 @@ struct Ctx {
   int64_t ws_off = 0, ws_peak = 0;
   bool dry = false;
   cudaStream_t stream;
+  // training-mode forward (BatchNorm batch statistics, dropout)
+  bool training = false;
+  float* params_mut = nullptr;           // same buffer as `params`, writable (BN moving averages, ActNorm init)
+  const float* const* masks = nullptr;   // injected dropout keep-masks (host array of device pointers) or null
+  int n_masks = 0, mask_cursor = 0;
+  uint64_t seed = 0;
+  int update_bn = 1;
 
   template <typename T>
   T* alloc(int64_t count) {
@@ -429,6 +436,10 @@ struct Ctx {
     return dry ? nullptr : reinterpret_cast<T*>(ws + o);
   }
   const float* P(const std::string& n) const { return dry ? nullptr : params + m->params[m->P(n)].offset; }
+  float* PM(const std::string& n) const {
+    if (!dry && !params_mut) VB_THROW("writable parameter buffer required (%s)", n.c_str());
+    return dry ? nullptr : params_mut + m->params[m->P(n)].offset;
+  }
   const __half* W(const std::string& n) const {
     auto it = m->pmats.find(n);
     if (it == m->pmats.end()) VB_THROW("unknown packed matrix %s", n.c_str());
@@ -676,6 +687,40 @@ static void run_pe(Ctx& c, float* out, int T, int D, float step) {
 }
 static int vt_pad(int T) { return cdiv(T, 64) * 64; }
 
+// Next dropout keep-mask in the reference's call order; injected (parity tests) or generated from (seed, site).
+static const float* next_mask(Ctx& c, int64_t n, float rate) {
+  const int site = c.mask_cursor++;
+  if (c.masks) {
+    if (site >= c.n_masks) VB_THROW("dropout mask %d requested but only %d supplied", site, c.n_masks);
+    return c.dry ? nullptr : c.masks[site];
+  }
+  float* mk = c.alloc<float>(n);
+  if (!c.dry) {
+    const int64_t thr = (n + 3) / 4;
+    dropout_mask_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, c.stream>>>(mk, n, rate, c.seed,
+                                                                                     static_cast<uint64_t>(site));
+    check_launch("dropout_mask");
+  }
+  return mk;
+}
+static void run_dropout(Ctx& c, const float* x, const float* mask, float* out_f32, __half* out_h, int64_t n) {
+  if (c.dry) return;
+  dropout_apply_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(x, mask, out_f32, out_h, n);
+  check_launch("dropout_apply");
+}
+// x = (x * mask2 + pw * table[t]) * mask3 -> fp32 + fp16  (posterior prenet tail in training mode, posterior.py:117-121)
+__global__ void prenet_tail_kernel(float* x, const float* __restrict__ mask2, const float* __restrict__ table,
+                                   const float* __restrict__ pw, const float* __restrict__ mask3, int seq_T, int C,
+                                   __half* __restrict__ out_h, long n) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long row = i / C;
+  const int c = static_cast<int>(i % C), t = static_cast<int>(row % seq_T);
+  const float v = (x[i] * mask2[i] + pw[0] * table[static_cast<long>(t) * C + c]) * mask3[i];
+  x[i] = v;
+  out_h[i] = __float2half_rn(v);
+}
+
 // ============================================================================ blocks
 struct Stream2 {   // fp32 residual stream + its fp16 operand copy, [rows, d]
   float* f;
@@ -781,6 +826,44 @@ static void xblk_fwd(Ctx& c, const std::string& pk, const std::string& pn, Strea
   }
 }
 
+// Conv1D wrapper of the reference: conv -> activation -> BatchNorm -> dropout (modules/utils.py:56-85).
+// Inference: BN folded into the GEMM epilogue.  Training: GEMM -> fp32 activations, batch statistics over all
+// (batch, time) rows incl. padding (deterministic two-stage reduction, fp64 finalise), moving-average update,
+// normalise + dropout + fp16 (hi/lo) operand for the next layer.
+static void conv_bn(Ctx& c, const std::string& pk, const std::string& pn, AOp a0, AOp a1, int B, int T, int cin, int C,
+                    int taps, int act, bool split, int block_n, float drop_rate, __half* out_h, __half* out_lo) {
+  GemmParams p = gp();
+  p.mode = EPI_PLAIN; p.N = C; p.act = act; segs_conv(p, taps, cin, split);
+  p.bias = c.P(pn + ".conv1d.bias");
+  if (!c.training) {
+    p.ch_scale = c.V(pk + ".bn_scale"); p.ch_shift = c.V(pk + ".bn_shift");
+    p.out_h = out_h; p.out_lo = out_lo; p.ld_h = C;
+    run_gemm(c, block_n, a0, a1, B, T, c.W(pk), c.WM(pk).K, C, p);
+    return;
+  }
+  const int64_t mark = c.ws_off;
+  const int64_t rows = static_cast<int64_t>(B) * T;
+  float* y = c.alloc<float>(rows * C);
+  p.out_f32 = y; p.ld_f32 = C;
+  run_gemm(c, block_n, a0, a1, B, T, c.W(pk), c.WM(pk).K, C, p);
+  const int rpt = 256, ntile = static_cast<int>(cdiv(static_cast<int>(rows), rpt));
+  float* partial = c.alloc<float>(static_cast<int64_t>(ntile) * 2 * C);
+  float* scale = c.alloc<float>(C);
+  float* shift = c.alloc<float>(C);
+  const float* mask = drop_rate > 0.f ? next_mask(c, rows * C, drop_rate) : nullptr;
+  if (!c.dry) {
+    colstats_partial_kernel<<<ntile, 256, 0, c.stream>>>(y, rows, C, rpt, partial);
+    bn_train_finalize_kernel<<<cdiv(C, 128), 128, 0, c.stream>>>(partial, ntile, rows, C, c.P(pn + ".bn.gamma"),
+                                                                c.P(pn + ".bn.beta"), c.PM(pn + ".bn.moving_mean"),
+                                                                c.PM(pn + ".bn.moving_variance"), 0.99f, 1e-3f, scale,
+                                                                shift, c.update_bn);
+    bn_apply_kernel<<<static_cast<unsigned>((rows * C + 255) / 256), 256, 0, c.stream>>>(y, scale, shift, mask, out_h, out_lo,
+                                                                                        rows * C, C);
+    check_launch("bn_train");
+  }
+  c.ws_off = mark;
+}
+
 // ============================================================================ modules
 // TransformerEncoder.call (modules/encoder.py:79-93), inference mode. Writes text_embd fp32 [B,Tt,E].
 static void encoder_fwd(Ctx& c, const int* texts, const int* t_len, int B, int Tt, float pos_step, float* text_embd) {
@@ -805,13 +888,10 @@ static void encoder_fwd(Ctx& c, const int* texts, const int* t_len, int B, int T
   }
   run_pe(c, pe, Tt, E, pos_step);
   int cin = h.embd_dim;
-  for (int i = 0; i < h.enc_n_conv; ++i) {   // ConvPreNet (modules/utils.py:21-38): conv -> relu -> BN
+  for (int i = 0; i < h.enc_n_conv; ++i) {   // ConvPreNet (modules/utils.py:21-38): conv -> relu -> BN -> dropout
     const std::string pk = "enc.conv" + std::to_string(i), pn = "text_encoder.prenet.conv_stack." + std::to_string(i);
-    GemmParams p = gp();
-    p.mode = EPI_PLAIN; p.N = E; p.act = 1; segs_conv(p, h.enc_conv_kernel, cin, false);
-    p.bias = c.P(pn + ".conv1d.bias"); p.ch_scale = c.V(pk + ".bn_scale"); p.ch_shift = c.V(pk + ".bn_shift");
-    p.out_h = xb; p.ld_h = E;
-    run_gemm(c, 128, AOp{xa, cin, cin}, AOp{}, B, Tt, c.W(pk), c.WM(pk).K, E, p);
+    conv_bn(c, pk, pn, AOp{xa, cin, cin}, AOp{}, B, Tt, cin, E, h.enc_conv_kernel, 1, false, 128, h.enc_pre_drop_rate, xb,
+            nullptr);
     std::swap(xa, xb);
     cin = E;
   }
@@ -824,6 +904,10 @@ static void encoder_fwd(Ctx& c, const int* texts, const int* t_len, int B, int T
     p.out_f32 = text_embd; p.ld_f32 = E; p.out_h = xb; p.ld_h = E;
     run_gemm(c, 128, AOp{xa, E, E}, AOp{}, 1, static_cast<int>(rows), c.W("enc.proj"), E, E, p);
     std::swap(xa, xb);
+    if (c.training && h.enc_pos_drop_rate > 0.f) {   // pe_dropout (encoder.py:87)
+      const float* mk = next_mask(c, rows * E, h.enc_pos_drop_rate);
+      run_dropout(c, text_embd, mk, text_embd, xa, rows * E);
+    }
   }
   for (int i = 0; i < h.enc_n_blk; ++i) {   // SelfAttentionBLK (modules/attention.py:405-415)
     const std::string pk = "enc.blk" + std::to_string(i), pn = "text_encoder.self_attentions." + std::to_string(i);
@@ -967,6 +1051,33 @@ static void prior_sample(Ctx& c, const float* text_embd, const int* t_len, const
   c.ws_off = mark;
 }
 
+// TransformerPrior.init (modules/prior.py:171-186): like sample, but every ActNorm is first initialised from the
+// statistics of its own input over ALL B*T positions (modules/flow.py:189-196); writes the parameters.
+static void prior_init(Ctx& c, const float* text_embd, const int* t_len, const int* z_len, int B, int Tt, int Tz, float* z) {
+  const vaenar_hparams_t& h = c.m->hp;
+  const int L = h.latent_dim;
+  const int64_t rows = static_cast<int64_t>(B) * Tz;
+  const int64_t mark = c.ws_off;
+  PriorBufs b = prior_setup(c, text_embd, B, Tt, Tz);
+  const int rpt = 256, ntile = cdiv(static_cast<int>(rows), rpt);
+  float* partial = c.alloc<float>(static_cast<int64_t>(ntile) * 2 * L);
+  float* Mf = c.dry ? nullptr : reinterpret_cast<float*>(c.packed + c.m->off_Mf);
+  float* cf = c.dry ? nullptr : reinterpret_cast<float*>(c.packed + c.m->off_cf);
+  for (int s = 0; s < h.prior_n_blk; ++s) {
+    const std::string g = "prior.glow." + std::to_string(s);
+    if (!c.dry) {
+      colstats_partial_kernel<<<ntile, 128, 0, c.stream>>>(z, rows, L, rpt, partial);
+      actnorm_init_kernel<<<1, FLOW_DIM, 0, c.stream>>>(partial, ntile, rows, c.PM(g + ".actnorm.log_scale"),
+                                                       c.PM(g + ".actnorm.bias"), c.P(g + ".linear.weight"),
+                                                       Mf + static_cast<int64_t>(s) * L * L, cf + s * L);
+      check_launch("actnorm_init");
+    }
+    flow_linear(c, z, b.zh, c.dry ? nullptr : Mf + static_cast<int64_t>(s) * L * L, c.dry ? nullptr : cf + s * L, rows);
+    coupling_step(c, s, false, z, b.zh, b.row_acc, b.x, b.xb, b.pe, b.kv, B, Tz, Tt, z_len, t_len);
+  }
+  c.ws_off = mark;
+}
+
 // TransformerPrior.log_probability (modules/prior.py:119-152)
 static void prior_logprob(Ctx& c, const float* z_in, const float* text_embd, const int* t_len, const int* z_len, int B,
                           int Tt, int Tz, float* logp) {
@@ -1020,19 +1131,45 @@ static void posterior_fwd(Ctx& c, const float* mels, const float* text_embd, con
     check_launch("reduce_mels");
     VB_CUDA(cudaMemsetAsync(row_acc, 0, rows * sizeof(float), c.stream));
   }
-  {  // PreNet dense1 + relu (modules/utils.py:13-18); dropout inactive (training=False)
-    GemmParams p = gp();
-    p.mode = EPI_PLAIN; p.N = d; p.act = 1; segs_plain(p, O);
-    p.bias = c.P("posterior.prenet.dense1.bias"); p.out_h = a1; p.ld_h = d;
-    run_gemm(c, 128, AOp{rm, O, O}, AOp{}, 1, static_cast<int>(rows), c.W("post.pre1"), kpad64(O), d, p);
-  }
-  {  // dense2 + relu, then + pos_weight * PE (posterior.py:118-121)
-    GemmParams p = gp();
-    p.mode = EPI_PLAIN; p.N = d; p.act = 1; segs_plain(p, d);
-    p.bias = c.P("posterior.prenet.dense2.bias");
-    p.seq_T = Tz; p.seq_B = B; p.add_table = pe; p.add_ld = d; p.add_scale = c.P("posterior.pos_weight");
-    p.out_f32 = x.f; p.ld_f32 = d; p.out_h = x.h; p.ld_h = d;
-    run_gemm(c, 128, AOp{a1, d, d}, AOp{}, 1, static_cast<int>(rows), c.W("post.pre2"), d, d, p);
+  if (!c.training) {
+    {  // PreNet dense1 + relu (modules/utils.py:13-18); dropout inactive (training=False)
+      GemmParams p = gp();
+      p.mode = EPI_PLAIN; p.N = d; p.act = 1; segs_plain(p, O);
+      p.bias = c.P("posterior.prenet.dense1.bias"); p.out_h = a1; p.ld_h = d;
+      run_gemm(c, 128, AOp{rm, O, O}, AOp{}, 1, static_cast<int>(rows), c.W("post.pre1"), kpad64(O), d, p);
+    }
+    {  // dense2 + relu, then + pos_weight * PE (posterior.py:118-121)
+      GemmParams p = gp();
+      p.mode = EPI_PLAIN; p.N = d; p.act = 1; segs_plain(p, d);
+      p.bias = c.P("posterior.prenet.dense2.bias");
+      p.seq_T = Tz; p.seq_B = B; p.add_table = pe; p.add_ld = d; p.add_scale = c.P("posterior.pos_weight");
+      p.out_f32 = x.f; p.ld_f32 = d; p.out_h = x.h; p.ld_h = d;
+      run_gemm(c, 128, AOp{a1, d, d}, AOp{}, 1, static_cast<int>(rows), c.W("post.pre2"), d, d, p);
+    }
+  } else {
+    // training: relu -> dropout after each dense (the PreNet inherits the Keras call-context training flag,
+    // posterior.py:117), then + pos_weight * PE, then pe_dropout (posterior.py:118-121)
+    const float* mk1 = next_mask(c, rows * d, h.posterior_pre_drop_rate);
+    const float* mk2 = next_mask(c, rows * d, h.posterior_pre_drop_rate);
+    const float* mk3 = next_mask(c, rows * d, h.posterior_pos_drop_rate);
+    {
+      GemmParams p = gp();
+      p.mode = EPI_PLAIN; p.N = d; p.act = 1; segs_plain(p, O);
+      p.bias = c.P("posterior.prenet.dense1.bias"); p.out_f32 = x.f; p.ld_f32 = d;
+      run_gemm(c, 128, AOp{rm, O, O}, AOp{}, 1, static_cast<int>(rows), c.W("post.pre1"), kpad64(O), d, p);
+      run_dropout(c, x.f, mk1, nullptr, a1, rows * d);
+    }
+    {
+      GemmParams p = gp();
+      p.mode = EPI_PLAIN; p.N = d; p.act = 1; segs_plain(p, d);
+      p.bias = c.P("posterior.prenet.dense2.bias"); p.out_f32 = x.f; p.ld_f32 = d;
+      run_gemm(c, 128, AOp{a1, d, d}, AOp{}, 1, static_cast<int>(rows), c.W("post.pre2"), d, d, p);
+      if (!c.dry) {
+        prenet_tail_kernel<<<static_cast<unsigned>((rows * d + 255) / 256), 256, 0, c.stream>>>(
+            x.f, mk2, pe, c.P("posterior.pos_weight"), mk3, Tz, d, x.h, rows * d);
+        check_launch("prenet_tail");
+      }
+    }
   }
   for (int i = 0; i < h.posterior_nblk; ++i)
     xblk_fwd(c, "post.blk" + std::to_string(i), "posterior.attentions." + std::to_string(i), x, xb, B, Tz, d, H, F, z_len, kv,
@@ -1097,11 +1234,8 @@ static void decoder_fwd(Ctx& c, const float* z, const float* text_embd, const in
   int cin = O;
   for (int i = 0; i < h.post_n_conv; ++i) {
     const std::string pk = "dec.post" + std::to_string(i), pn = "decoder.postnet.conv_stack." + std::to_string(i);
-    GemmParams p = gp();
-    p.mode = EPI_PLAIN; p.N = C; p.act = (i < h.post_n_conv - 1) ? 2 : 0; segs_conv(p, h.post_kernel, cin, true);
-    p.bias = c.P(pn + ".conv1d.bias"); p.ch_scale = c.V(pk + ".bn_scale"); p.ch_shift = c.V(pk + ".bn_shift");
-    p.out_h = out_h; p.out_lo = out_l; p.ld_h = C;
-    run_gemm(c, 256, AOp{in_h, cin, cin}, AOp{in_l, cin, cin}, B, Tm, c.W(pk), c.WM(pk).K, C, p);   // one wave: 112 CTAs
+    conv_bn(c, pk, pn, AOp{in_h, cin, cin}, AOp{in_l, cin, cin}, B, Tm, cin, C, h.post_kernel,
+            (i < h.post_n_conv - 1) ? 2 : 0, true, 256, h.post_drop_rate, out_h, out_l);   // 256: one wave of 112 CTAs
     in_h = out_h; in_l = out_l;
     out_h = (in_h == pa_h) ? pb_h : pa_h;
     out_l = (in_l == pa_l) ? pb_l : pa_l;
@@ -1216,6 +1350,20 @@ static void inference_fwd(Ctx& c, const int* texts, const int* t_len, const int*
     VB_CUDA(cudaEventRecord(c.m->ev_join, c1.stream));
     VB_CUDA(cudaStreamWaitEvent(c.stream, c.m->ev_join, 0));
   }
+  c.ws_off = mark;
+}
+
+// VAENAR.init (models/models.py:212-226): training=True, rf = max_reduction_factor
+static void init_fwd(Ctx& c, const int* texts, const int* t_len, const int* z_len, int B, int Tt, int Tz, float* z_io,
+                     float* mel) {
+  const vaenar_hparams_t& h = c.m->hp;
+  const int rf = h.max_reduction_factor;
+  const int64_t mark = c.ws_off;
+  float* emb = c.alloc<float>(static_cast<int64_t>(B) * Tt * h.enc_hidden);
+  float* ini = c.alloc<float>(static_cast<int64_t>(B) * Tz * rf * h.out_dim);
+  encoder_fwd(c, texts, t_len, B, Tt, h.mel_text_len_ratio / static_cast<float>(rf), emb);
+  prior_init(c, emb, t_len, z_len, B, Tt, Tz, z_io);
+  decoder_fwd(c, z_io, emb, z_len, t_len, B, Tt, Tz, rf, ini, mel, nullptr);
   c.ws_off = mark;
 }
 
@@ -1360,6 +1508,10 @@ int64_t vaenar_workspace_bytes(vaenar_handle_t h, int B, int T_text, int T_z, in
     inference_fwd(c, nullptr, nullptr, nullptr, B, T_text, T_z, rf, nullptr, nullptr, nullptr, nullptr, nullptr);
     elbo_fwd(c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, B, T_text, T_z * rf, T_z, rf, nullptr, nullptr, nullptr,
              nullptr, nullptr);
+    c.training = true;   // training-mode forward needs fp32 conv activations, statistics and masks
+    c.mask_cursor = 0;
+    elbo_fwd(c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, B, T_text, T_z * rf, T_z, rf, nullptr, nullptr, nullptr,
+             nullptr, nullptr);
     return align_up(c.ws_peak, 1024) + 4096;
   } catch (const EngineError& e) {
     g_err = e.msg;
@@ -1449,6 +1601,38 @@ int vaenar_elbo_fwd(vaenar_handle_t h, const float* params, const void* packed, 
   Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
   elbo_fwd(c, texts, mels, mel_lengths, text_lengths, z_lengths, eps, B, T_text, T_mel, T_z, rf, mel_out, l2, kl,
            length_loss, alignments);
+  API_END
+}
+
+static void apply_train_opts(Ctx& c, float* params, const vaenar_train_opts_t* o) {
+  c.training = true;
+  c.params_mut = params;
+  c.mask_cursor = 0;
+  if (o) {
+    c.masks = o->masks; c.n_masks = o->n_masks; c.seed = o->seed; c.update_bn = o->update_bn_stats;
+  }
+}
+
+int vaenar_elbo_fwd_train(vaenar_handle_t h, float* params, const void* packed, void* ws, int64_t ws_bytes,
+                          const int32_t* texts, const float* mels, const int32_t* mel_lengths,
+                          const int32_t* text_lengths, const int32_t* z_lengths, const float* eps, int B, int T_text,
+                          int T_mel, int T_z, int rf, const vaenar_train_opts_t* opts, float* mel_out, float* l2,
+                          float* kl, float* length_loss, float* alignments, void* stream) {
+  API_BEGIN
+  Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
+  apply_train_opts(c, params, opts);
+  elbo_fwd(c, texts, mels, mel_lengths, text_lengths, z_lengths, eps, B, T_text, T_mel, T_z, rf, mel_out, l2, kl,
+           length_loss, alignments);
+  API_END
+}
+
+int vaenar_init(vaenar_handle_t h, float* params, void* packed, void* ws, int64_t ws_bytes, const int32_t* texts,
+                const int32_t* text_lengths, const int32_t* z_lengths, int B, int T_text, int T_z,
+                const vaenar_train_opts_t* opts, float* z_io, float* mel, void* stream) {
+  API_BEGIN
+  Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
+  apply_train_opts(c, params, opts);
+  init_fwd(c, texts, text_lengths, z_lengths, B, T_text, T_z, z_io, mel);
   API_END
 }
 

@@ -380,6 +380,101 @@ __global__ void l2_loss_kernel(const float* __restrict__ rec, int rec_T, const f
   }
 }
 
+// ------------------------------------------------------------------ training-mode BatchNorm / dropout / ActNorm init
+// Per-channel partial sums over a tile of rows: partial[tile][0][c] = sum x, partial[tile][1][c] = sum x^2.
+// (Keras BatchNormalization in training mode normalises with the batch mean / population variance over
+// (batch, time) INCLUDING padded frames, modules/utils.py:72,79-83.)
+__global__ void colstats_partial_kernel(const float* __restrict__ x, long rows, int C, int rows_per_tile,
+                                        float* __restrict__ partial) {
+  const long r0 = static_cast<long>(blockIdx.x) * rows_per_tile;
+  const long r1 = min(rows, r0 + rows_per_tile);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (long r = r0; r < r1; ++r) {
+      const float v = x[r * C + c];
+      s += v;
+      q = fmaf(v, v, q);
+    }
+    partial[(static_cast<long>(blockIdx.x) * 2 + 0) * C + c] = s;
+    partial[(static_cast<long>(blockIdx.x) * 2 + 1) * C + c] = q;
+  }
+}
+// mean / population variance (float64 accumulation over the tile partials, fixed order => deterministic),
+// folded affine for the apply kernel, and the moving-average update  m <- m * momentum + batch * (1 - momentum).
+__global__ void bn_train_finalize_kernel(const float* __restrict__ partial, int ntile, long rows, int C,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float* __restrict__ moving_mean, float* __restrict__ moving_var, float momentum,
+                                         float eps, float* __restrict__ scale, float* __restrict__ shift, int update) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int t = 0; t < ntile; ++t) {
+    s += partial[(static_cast<long>(t) * 2 + 0) * C + c];
+    q += partial[(static_cast<long>(t) * 2 + 1) * C + c];
+  }
+  const double mean = s / static_cast<double>(rows);
+  const double var = fmax(q / static_cast<double>(rows) - mean * mean, 0.0);
+  const float sc = gamma[c] * rsqrtf(static_cast<float>(var) + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] - static_cast<float>(mean) * sc;
+  if (update) {
+    moving_mean[c] = moving_mean[c] * momentum + static_cast<float>(mean) * (1.f - momentum);
+    moving_var[c] = moving_var[c] * momentum + static_cast<float>(var) * (1.f - momentum);
+  }
+}
+// y * scale[c] + shift[c], times the dropout mask (values 0 or 1/(1-rate)); fp16 (+ split lo) operand for the next conv
+__global__ void bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const float* __restrict__ mask,
+                                __half* __restrict__ out_h, __half* __restrict__ out_lo, long n, int C) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C);
+  float v = y[i] * scale[c] + shift[c];
+  if (mask) v *= mask[i];
+  const __half h = __float2half_rn(v);
+  out_h[i] = h;
+  if (out_lo) out_lo[i] = __float2half_rn(v - __half2float(h));
+}
+// x * mask -> fp32 (optional, may alias x) and fp16 copies
+__global__ void dropout_apply_kernel(const float* x, const float* __restrict__ mask, float* out_f32,
+                                     __half* __restrict__ out_h, long n) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i] * mask[i];
+  if (out_f32) out_f32[i] = v;
+  if (out_h) out_h[i] = __float2half_rn(v);
+}
+// ActNormFlow.init (modules/flow.py:189-196): data-dependent log_scale = log(1/(std+1e-8)), bias = -mean/(std+1e-8)
+// from the population statistics over ALL positions, written into the parameter buffer, plus the folded forward map
+// of this step (Mf = diag(e^s) W, cf = b W) so that the flow can continue immediately.  One CTA of 128 threads.
+__global__ void actnorm_init_kernel(const float* __restrict__ partial, int ntile, long rows, float* __restrict__ log_scale,
+                                    float* __restrict__ bias, const float* __restrict__ W, float* __restrict__ Mf,
+                                    float* __restrict__ cf) {
+  __shared__ float s_es[FLOW_DIM], s_b[FLOW_DIM];
+  const int j = threadIdx.x;
+  double s = 0.0, q = 0.0;
+  for (int t = 0; t < ntile; ++t) {
+    s += partial[(static_cast<long>(t) * 2 + 0) * FLOW_DIM + j];
+    q += partial[(static_cast<long>(t) * 2 + 1) * FLOW_DIM + j];
+  }
+  const double mean = s / static_cast<double>(rows);
+  const float sd = sqrtf(static_cast<float>(fmax(q / static_cast<double>(rows) - mean * mean, 0.0)));
+  const float ls = logf(1.0f / (sd + 1e-8f));
+  const float b = -static_cast<float>(mean) / (sd + 1e-8f);
+  log_scale[j] = ls;
+  bias[j] = b;
+  s_es[j] = expf(ls);
+  s_b[j] = b;
+  __syncthreads();
+  float c = 0.f;
+  for (int i = 0; i < FLOW_DIM; ++i) {
+    const float w = W[i * FLOW_DIM + j];
+    Mf[i * FLOW_DIM + j] = s_es[i] * w;
+    c += s_b[i] * w;
+  }
+  cf[j] = c;
+}
+
 // ------------------------------------------------------------------ counter-based N(0,1) generator
 // Philox4x32-10 + Box-Muller; element i of a stream is a pure function of (seed, stream, i).
 __device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,
@@ -410,6 +505,26 @@ __global__ void randn_kernel(float* __restrict__ out, long n, uint64_t seed, uin
   sincosf(6.283185307179586f * u3, &s1, &co1);
   const float v[4] = {r0 * co0 * stddev, r0 * s0 * stddev, r1 * co1 * stddev, r1 * s1 * stddev};
   for (int j = 0; j < 4 && i4 * 4 + j < n; ++j) out[i4 * 4 + j] = v[j];
+}
+
+// Inverted-dropout keep mask (Keras Dropout): 0 with probability rate, else 1/(1-rate); same Philox stream layout.
+__global__ void dropout_mask_kernel(float* __restrict__ out, long n, float rate, uint64_t seed, uint64_t stream) {
+  const long i4 = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= n) return;
+  uint32_t c0 = static_cast<uint32_t>(i4), c1 = static_cast<uint32_t>(i4 >> 32);
+  uint32_t c2 = static_cast<uint32_t>(stream), c3 = static_cast<uint32_t>(stream >> 32) ^ 0x5D0Fu;
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const uint32_t cs[4] = {c0, c1, c2, c3};
+  const float keep = 1.0f / (1.0f - rate);
+  for (int j = 0; j < 4 && i4 * 4 + j < n; ++j) {
+    const float u = static_cast<float>(cs[j]) * 2.3283064365386963e-10f;
+    out[i4 * 4 + j] = (u >= rate) ? keep : 0.f;
+  }
 }
 
 }  // namespace vb

@@ -19,7 +19,7 @@ from collections import OrderedDict
 import torch
 
 from . import _lib
-from ._lib import HParamsStruct, VaenarError, check
+from ._lib import HParamsStruct, TrainOpts, VaenarError, check
 
 
 def _tf(hps_section):
@@ -42,6 +42,11 @@ def hparams_struct(hps) -> HParamsStruct:
     s.latent_dim, s.out_dim = C.latent_dim, C.output_dim
     s.max_reduction_factor, s.final_reduction_factor = C.max_reduction_factor, C.final_reduction_factor
     s.mel_text_len_ratio = float(C.mel_text_len_ratio)
+    s.enc_pre_drop_rate = float(getattr(E, "pre_drop_rate", 0.1))
+    s.enc_pos_drop_rate = float(getattr(E, "pos_drop_rate", 0.1))
+    s.posterior_pre_drop_rate = float(getattr(Q, "pre_drop_rate", 0.5))
+    s.posterior_pos_drop_rate = float(getattr(Q, "pos_drop_rate", 0.2))
+    s.post_drop_rate = float(getattr(D, "post_drop_rate", 0.2))
     for name, temp in (("Encoder", getattr(E, "attention_temperature", 1.0)),
                        ("Decoder", getattr(D, "attention_temperature", 1.0)),
                        ("Posterior", getattr(Q, "temperature", 1.0)), ("Prior", getattr(R, "temperature", 1.0))):
@@ -220,6 +225,21 @@ class VAENAR:
                                      self._stream()))
         return out
 
+    def _train_opts(self, dropout_masks, update_bn_stats=True):
+        """vaenar_train_opts_t: injected dropout keep-masks (parity tests) or on-device generation from the seed."""
+        o = TrainOpts()
+        self._noise_calls += 1
+        o.seed = (self._seed << 20) + self._noise_calls
+        o.update_bn_stats = 1 if update_bn_stats else 0
+        keep = None
+        if dropout_masks is not None:
+            keep = [self._f32(m) for m in dropout_masks]
+            arr = (ctypes.c_void_p * len(keep))(*[m.data_ptr() for m in keep])
+            o.n_masks = len(keep)
+            o.masks = ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))
+            keep.append(arr)
+        return o, keep
+
     @staticmethod
     def _no_training(training, what):
         if training:
@@ -379,10 +399,9 @@ class VAENAR:
         return mel, self._ali_dict(ali)
 
     def call(self, inputs, mel_targets, mel_lengths, text_lengths=None, reduction_factor=2, training=None,
-             reduce_loss=None, eps=None, return_alignments=True):
+             reduce_loss=None, eps=None, return_alignments=True, dropout_masks=None, update_bn_stats=True):
         """VAENAR.call (models/models.py:105-197) -> (decoded_outs, l2_loss, kl_divergence, length_loss,
         dec_alignments).  ``eps`` (optional) injects the posterior noise [B,1,T_z,latent] for parity tests."""
-        self._no_training(training, "VAENAR.call")
         rf = int(reduction_factor)
         texts = self._i32(inputs)
         mels = self._f32(mel_targets)
@@ -400,19 +419,50 @@ class VAENAR:
         kl = torch.empty_like(l2)
         ll = torch.empty_like(l2)
         ali = torch.empty(nb, B, H, Tz, Tt, dtype=torch.float32, device=self.device) if return_alignments else None
-        check(self._lib.vaenar_elbo_fwd(self._h, self._p(self._flat), self._p(self._packed), self._p(self._ws),
-                                        self._ws.numel(), self._p(texts), self._p(mels), self._p(m_len), self._p(t_len),
-                                        self._p(z_len), self._p(e), B, Tt, Tm, Tz, rf, self._p(mel), self._p(l2),
-                                        self._p(kl), self._p(ll), self._p(ali), self._stream()))
+        if training:
+            # forward with training=True semantics (BN batch statistics + moving-average update, dropout).
+            # NOTE: forward only -- the backward pass / optimiser step are not implemented on the CUDA path yet.
+            opts, keep = self._train_opts(dropout_masks, update_bn_stats)
+            check(self._lib.vaenar_elbo_fwd_train(
+                self._h, self._p(self._flat), self._p(self._packed), self._p(self._ws), self._ws.numel(), self._p(texts),
+                self._p(mels), self._p(m_len), self._p(t_len), self._p(z_len), self._p(e), B, Tt, Tm, Tz, rf,
+                ctypes.byref(opts), self._p(mel), self._p(l2), self._p(kl), self._p(ll), self._p(ali), self._stream()))
+            if update_bn_stats:
+                self._dirty = True          # folded inference BatchNorm constants are stale now
+        else:
+            check(self._lib.vaenar_elbo_fwd(self._h, self._p(self._flat), self._p(self._packed), self._p(self._ws),
+                                            self._ws.numel(), self._p(texts), self._p(mels), self._p(m_len),
+                                            self._p(t_len), self._p(z_len), self._p(e), B, Tt, Tm, Tz, rf, self._p(mel),
+                                            self._p(l2), self._p(kl), self._p(ll), self._p(ali), self._stream()))
         if reduce_loss:
             l2, kl, ll = l2.mean(), kl.mean(), ll.mean()
         return mel, l2, kl, ll, self._ali_dict(ali)
 
     __call__ = call
 
-    def init(self, text_inputs, mel_lengths, text_lengths=None):
-        raise NotImplementedError("VAENAR.init (models/models.py:212-226) belongs to the training path, which is "
-                                  "not implemented on the CUDA path yet")
+    def init(self, text_inputs, mel_lengths, text_lengths=None, epsilon=None, dropout_masks=None):
+        """VAENAR.init (models/models.py:212-226): data-dependent ActNorm initialisation at
+        rf = max_reduction_factor with training=True (dropout + BN batch statistics); returns the predicted mel.
+        ``epsilon`` / ``dropout_masks`` optionally inject the random draws (parity tests)."""
+        rf = self.max_reduction_factor
+        texts = self._i32(text_inputs)
+        B, Tt = texts.shape
+        z_len_host = (torch.as_tensor(mel_lengths).to(torch.int64) + rf - 1) // rf
+        Tz = self._max_len(z_len_host)
+        z_len = self._i32(z_len_host)
+        t_len = self._i32(text_lengths)
+        self._prepare(B, Tt, Tz, rf)
+        L, O = self._hp.latent_dim, self._hp.out_dim
+        z = self._noise((B, Tz, L)) if epsilon is None else self._f32(epsilon).contiguous().clone()
+        if tuple(z.shape) != (B, Tz, L):
+            raise VaenarError(f"epsilon shape {tuple(z.shape)} != {(B, Tz, L)}")
+        mel = torch.empty(B, Tz * rf, O, dtype=torch.float32, device=self.device)
+        opts, keep = self._train_opts(dropout_masks, True)
+        check(self._lib.vaenar_init(self._h, self._p(self._flat), self._p(self._packed), self._p(self._ws),
+                                    self._ws.numel(), self._p(texts), self._p(t_len), self._p(z_len), B, Tt, Tz,
+                                    ctypes.byref(opts), self._p(z), self._p(mel), self._stream()))
+        self._dirty = True                  # ActNorm parameters and BN moving averages changed
+        return mel
 
 
 class InferenceSession:
