@@ -1,0 +1,15 @@
+"""Tiny run of every C-ABI path (inference, call eval, call training-forward, init) for compute-sanitizer."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from oracle import vaenar_oracle as O
+from oracle.hparams import LJHPS as OH
+from vaenar_tts_b200 import VAENAR, LJHPS
+P = O.init_params(OH, seed=1, zero_init_std=0.02)
+m = VAENAR(LJHPS, device="cuda"); m.load_state_dict(P)
+texts, mels, t_len, m_len = O.synthetic_batch(OH, 4, 20, 70)
+mel, ali = m.inference(texts, m_len, t_len, reduction_factor=2)
+out = m(inputs=texts, mel_targets=mels, mel_lengths=m_len, text_lengths=t_len, reduction_factor=2, training=False, reduce_loss=True)
+out2 = m(inputs=texts, mel_targets=mels, mel_lengths=m_len, text_lengths=t_len, reduction_factor=2, training=True, reduce_loss=True)
+m.init(texts, m_len, t_len)
+torch.cuda.synchronize(); print("ok", float(mel.abs().mean()), float(out[2]))
