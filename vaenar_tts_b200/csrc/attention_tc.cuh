@@ -120,6 +120,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // PDL: prologue overlapped the previous kernel's tail
+  pdl_wait();
   const uint32_t tmem_S = tmem_base;          // two buffers: columns [0,128) and [128,256)
   const uint32_t tmem_O = tmem_base + 256;    // columns [256, 320)
 

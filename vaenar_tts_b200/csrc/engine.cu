@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -461,6 +462,7 @@ struct KernelStat {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
 };
 static long g_launch_count = 0;
+static bool g_use_pdl = true;   // programmatic dependent launch between the tensor-core kernels (VAENAR_NO_PDL=1 disables)
 static unsigned long long* g_dbg_cursor = nullptr;   // tuning aid: per-CTA phase timestamps of GEMM launches
 static unsigned long long* g_dbg_base = nullptr;
 static std::vector<std::string> g_dbg_launches;
@@ -513,6 +515,7 @@ struct ProfileScope {
 static void set_attrs(vaenar_model* m) {
   static bool done = false;
   if (done) return;
+  if (const char* e = getenv("VAENAR_NO_PDL")) g_use_pdl = !(e[0] == '1');
 #define VB_SET_ATTR(BN, MODE, FEAT)                                                                  \
   VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, (FEAT)>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                GemmCfg<BN>::kSmemBytes));
@@ -600,13 +603,15 @@ static void run_gemm(Ctx& c, int block_n, AOp a0, AOp a1, int batches, int rows,
   cfg.gridDim = grid;
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.stream = c.stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = p.ln_cluster ? 2 : 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: the kernel calls griddepcontrol.wait
+  attr[1].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t le = cudaErrorInvalidValue;
   bool launched = false;
   // feature mask of this call (EPI_PLAIN); a specialised instance is used when one exists, else the run-time one
@@ -669,8 +674,20 @@ static void run_attention(Ctx& c, int B, int H, const AttnCall& a) {
   const double work = static_cast<double>(B) * H * a.Tq * a.Tk;
   ProfileScope prof(a.causal ? "attn_self" : (a.ali ? "attn_cross_ali" : "attn_cross"), 4.0 * work * ATT_D,
                     static_cast<double>(B) * H * ATT_D * 2 * (2.0 * a.Tq + 2.0 * a.Tk) + (a.ali ? work * 4 : 0), c.stream);
-  if (a.ali) attention_tc_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, c.stream>>>(tQ, tK, tV, p);
-  else attention_tc_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, c.stream>>>(tQ, tK, tV, p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(ATT_THREADS);
+  cfg.dynamicSmemBytes = ATT_SMEM;
+  cfg.stream = c.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t le = a.ali ? cudaLaunchKernelEx(&cfg, attention_tc_kernel<true>, tQ, tK, tV, p)
+                               : cudaLaunchKernelEx(&cfg, attention_tc_kernel<false>, tQ, tK, tV, p);
+  if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(attention_tc_kernel) failed: %s", cudaGetErrorString(le));
   check_launch("attention_tc_kernel");
 }
 

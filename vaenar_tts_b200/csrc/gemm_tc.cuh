@@ -164,6 +164,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (p.ln_cluster) cluster_sync_all();   // peer barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
+  // from here on we touch memory produced by it.
+  pdl_launch_dependents();
+  pdl_wait();
   if (dbg && threadIdx.x == 64) dbg[1] = gtime();
 
   if (warp == 0) {

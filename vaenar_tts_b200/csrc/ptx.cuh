@@ -97,6 +97,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// wait: block until every prerequisite grid has completed and its memory is visible (no-op without the launch attribute)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// allow the dependent grid to start launching (its own pdl_wait still orders its reads after our completion)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
