@@ -144,6 +144,14 @@ int vaenar_init(vaenar_handle_t h, float* params, void* packed, void* ws, int64_
                 const int32_t* text_lengths, const int32_t* z_lengths, int B, int T_text, int T_z,
                 const vaenar_train_opts_t* opts, float* z_io, float* mel, void* stream);
 
+/* Optimiser half of train_step (train.py:116-117,137): Keras Adam over the flat parameter buffer, one fused launch.
+ * `trainable_mask` (device, one byte per float; host copy from vaenar_trainable_mask) skips the BatchNorm moving
+ * statistics and padding; grad_scale folds the 1/world_size of the data-parallel gradient mean.  The gradients
+ * themselves (backward pass) are not produced by this library yet. */
+int vaenar_trainable_mask(vaenar_handle_t h, uint8_t* host_mask);
+int vaenar_adam_step(float* params, const float* grads, float* m, float* v, const uint8_t* trainable_mask, int64_t n,
+                     int64_t step, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
 /* N(0, stddev) noise from the counter-based generator (replaces tf.random.normal at
  * modules/posterior.py:35 and modules/prior.py:35). */
 int vaenar_randn(float* out, int64_t n, uint64_t seed, uint64_t stream_id, float stddev, void* stream);

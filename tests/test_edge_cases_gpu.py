@@ -97,3 +97,25 @@ def test_temperature_zero_is_deterministic():
     zmask = O.sequence_mask(z_len, z1.shape[1], torch.float32)[:, :, None]
     assert float(((z1.cpu() - zr).abs() * zmask).max()) < 2e-2
     assert rel(lp1, lpr) < REL_TOL
+
+
+def test_adam_step_matches_keras_formula():
+    """vaenar_adam_step vs the oracle's Keras-Adam restatement (train.py:116-117) over three steps; BatchNorm moving
+    statistics must not move."""
+    from vaenar_tts_b200 import VAENAR, LJHPS
+    m = VAENAR(LJHPS, device="cuda", seed=3)
+    p0 = m.flat_parameters().clone()
+    ref_p, ref_m, ref_v = p0.cpu().double(), torch.zeros_like(p0).cpu().double(), torch.zeros_like(p0).cpu().double()
+    g = torch.Generator().manual_seed(0)
+    for step in (1, 2, 3):
+        grads = torch.randn(p0.numel(), generator=g) * 1e-3
+        m.apply_gradients(grads, step)
+        ref_p, ref_m, ref_v = O.adam_update(ref_p, grads.double(), ref_m, ref_v, step)
+    mask = m._trainable_mask.cpu().bool()
+    got = m.flat_parameters().cpu().double()
+    # fp32 kernel vs float64 restatement: one ulp of the largest parameters (gamma = 1) is 1.2e-7
+    assert float((got[mask] - ref_p[mask]).abs().max()) < 5e-7
+    assert float(((got[mask] - p0.cpu().double()[mask]) - (ref_p[mask] - p0.cpu().double()[mask])).abs().max()) < 5e-7
+    assert torch.equal(got[~mask].float(), p0.cpu()[~mask])
+    sd = m.state_dict()
+    assert float(sd["decoder.postnet.conv_stack.0.bn.moving_variance"].min()) == 1.0

@@ -36,6 +36,8 @@ def test_dense_plain(M, K, N, block_n):
 @pytest.mark.parametrize("split_cluster", [False, True])
 @pytest.mark.parametrize("M,K,N", [(300, 512, 256), (200, 1024, 256), (148, 768, 512), (131, 1024, 512)])
 def test_dense_layernorm(M, K, N, split_cluster):
+    if N == 512 and not split_cluster:
+        pytest.skip("N=512 LayerNorm is only built as the 2-CTA cluster split (2 x 256 columns)")
     """GEMM + bias + residual + LayerNorm epilogue; split_cluster: N split over a 2-CTA cluster with the
     row statistics exchanged through distributed shared memory."""
     import gpu_util as G

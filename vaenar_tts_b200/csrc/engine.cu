@@ -509,7 +509,7 @@ struct ProfileScope {
   X(128, EPI_PLAIN, F_BIAS | F_RELU | F_TABLE | F_OUT_F32 | F_OUT_H)                                  \
   X(128, EPI_PLAIN, F_BIAS | F_OUT_F32 | F_OUT_H | F_OUT_LO)                                          \
   X(128, EPI_PLAIN, F_BIAS | F_RES | F_OUT_F32)                                                       \
-  X(128, EPI_LN, 0) X(256, EPI_LN, 0) X(512, EPI_LN, 0)                                              \
+  X(128, EPI_LN, 0) X(256, EPI_LN, 0)                                                                \
   X(256, EPI_QKV, F_OUT_H) X(128, EPI_COUPLING, 0) X(256, EPI_POSTERIOR, 0)
 
 static void set_attrs(vaenar_model* m) {
@@ -601,7 +601,7 @@ static void run_gemm(Ctx& c, int block_n, AOp a0, AOp a1, int batches, int rows,
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(gemm_threads(p.mode));
   cfg.stream = c.stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1650,6 +1650,27 @@ int vaenar_init(vaenar_handle_t h, float* params, void* packed, void* ws, int64_
   Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
   apply_train_opts(c, params, opts);
   init_fwd(c, texts, text_lengths, z_lengths, B, T_text, T_z, z_io, mel);
+  API_END
+}
+
+int vaenar_trainable_mask(vaenar_handle_t h, uint8_t* host_mask) {
+  API_BEGIN
+  if (!h || !host_mask) VB_THROW("null argument");
+  memset(host_mask, 0, static_cast<size_t>(h->param_floats));
+  for (const ParamInfo& pi : h->params)
+    if (pi.trainable) memset(host_mask + pi.offset, 1, static_cast<size_t>(pi.numel));
+  API_END
+}
+
+int vaenar_adam_step(float* params, const float* grads, float* m, float* v, const uint8_t* trainable_mask, int64_t n,
+                     int64_t step, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  API_BEGIN
+  if (step < 1) VB_THROW("Adam step counts from 1");
+  const double lr_t = static_cast<double>(lr) * std::sqrt(1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(step))) /
+                      (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(step)));
+  adam_step_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      params, grads, m, v, trainable_mask, n, static_cast<float>(lr_t), beta1, beta2, eps, grad_scale);
+  check_launch("adam_step");
   API_END
 }
 

@@ -22,7 +22,8 @@ constexpr int kMaxSegs = 16;
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
 constexpr int GEMM_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int GEMM_EPI_THREADS = 256;
+constexpr int GEMM_THREADS_LN = 576;       // LayerNorm epilogue: warps 2..17 (four per TMEM lane quadrant)
+__host__ __device__ constexpr int gemm_threads(int mode) { return mode == 1 /*EPI_LN*/ ? GEMM_THREADS_LN : GEMM_THREADS; }
 
 enum EpiMode : int {
   EPI_PLAIN = 0,     // act(acc + bias) [*scale + shift] [+ a * table[t]] [+ residual] -> f32 / f16 / f16-lo
@@ -115,7 +116,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 
 template <int BLOCK_N, int MODE, uint32_t FEAT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(MODE), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
@@ -277,16 +278,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     };
 
-    // LayerNorm: fetch this warp's first residual chunk into registers while the mainloop is still running
-    uint4 pre[16];
+    // LayerNorm (16 epilogue warps): column group of this warp and its first residual chunk, fetched into registers
+    // while the mainloop is still running
+    static_assert(MODE != EPI_LN || BLOCK_N == 128 || BLOCK_N == 256, "LayerNorm epilogue: BLOCK_N 128 or 256");
+    constexpr int NCH = (MODE == EPI_LN) ? BLOCK_N / 128 : 1;    // 32-column chunks per LayerNorm warp
+    const int grp = (warp - 2) >> 2;                             // 0..3 (LayerNorm) / 0..1 (other modes, == half)
+    uint4 pre[8];
     if constexpr (MODE == EPI_LN) {
-      const int n0p = n_tile * BLOCK_N + half * 64;
+      const int n0p = n_tile * BLOCK_N + grp * 32;
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int row = (it & 7) * 4 + (lane >> 3), chunk = lane & 7;
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + (lane >> 3), chunk = lane & 7;
         pre[it] = make_uint4(0u, 0u, 0u, 0u);
-        if (row < rows_here)
-          pre[it] = __ldg(reinterpret_cast<const uint4*>(p.residual + (grow0 + row) * p.res_ld + n0p + (it >> 3) * 32 + chunk * 4));
+        if (row < rows_here) pre[it] = __ldg(reinterpret_cast<const uint4*>(p.residual + (grow0 + row) * p.res_ld + n0p + chunk * 4));
       }
     }
     mbar_wait(tmem_full_bar, 0);
@@ -404,57 +408,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
     } else if constexpr (MODE == EPI_LN) {
-      // pass A: x = acc + bias + residual; row sum and sum of squares in one sweep; x written back to TMEM
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f}, sq4[4] = {0.f, 0.f, 0.f, 0.f};
-      const int nbase = n_tile * BLOCK_N;            // column offset of this CTA (cluster split of N)
+      // 16 warps: warp (quad, grp) owns rows quad*32.. and the 32-column chunks {ci*128 + grp*32}.  The values stay in
+      // registers between the statistics sweep and the normalisation (no TMEM write-back).
+      uint8_t* l_f32 = smem_a + (warp - 2) * 6144;          // [32 rows x 128 B] fp32 / residual slab (swizzled)
+      uint8_t* l_h = l_f32 + 4096;                          // [32 rows x 64 B] fp16 slab, chunk ^= (row >> 1) & 3
+      float* lred = reinterpret_cast<float*>(smem_a + 16 * 6144);   // [2][4][128] row-statistic exchange
+      auto ln_bar = []() { asm volatile("bar.sync 1, 512;" ::: "memory"); };
+      const int nbase = n_tile * BLOCK_N;                   // column offset of this CTA (cluster split of N)
       const float inv_n = 1.f / static_cast<float>(p.ln_cluster ? 2 * BLOCK_N : BLOCK_N);
       const uint32_t peer = cluster_ctarank() ^ 1u;
-      for (int dc = half; dc < BLOCK_N / 64; dc += 2) {
-        const int n0 = nbase + dc * 64;
-        __syncwarp();
-        if (dc == half) {
+      float xs[NCH][32];
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f}, sq4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int it = 0; it < 16; ++it)
-            *sw(s_res + (it >> 3) * 4096, (it & 7) * 4 + (lane >> 3), lane & 7) = pre[it];
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int col0 = ci * 128 + grp * 32;
+        const int n0 = nbase + col0;
+        __syncwarp();
+        if (ci == 0) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) *sw(l_f32, it * 4 + (lane >> 3), lane & 7) = pre[it];
         } else {
-          load_f32_slab(s_res, p.residual, p.res_ld, n0, 64);
-          load_f32_slab(s_res + 4096, p.residual, p.res_ld, n0 + 32, 32);
+          load_f32_slab(l_f32, p.residual, p.res_ld, n0, 32);
         }
-        tmem_ld32(taddr + dc * 64, v);
-        tmem_ld32(taddr + dc * 64 + 32, w);
+        tmem_ld32(taddr + col0, v);
         tmem_wait_ld();
         __syncwarp();
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t* acc = hh ? w : v;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + hh * 32 + g * 4));
-            const uint4 rq = *sw(s_res + hh * 4096, lane, g);
-            const float x0 = __uint_as_float(acc[g * 4 + 0]) + bq.x + __uint_as_float(rq.x);
-            const float x1 = __uint_as_float(acc[g * 4 + 1]) + bq.y + __uint_as_float(rq.y);
-            const float x2 = __uint_as_float(acc[g * 4 + 2]) + bq.z + __uint_as_float(rq.z);
-            const float x3 = __uint_as_float(acc[g * 4 + 3]) + bq.w + __uint_as_float(rq.w);
-            sum4[0] += x0; sum4[1] += x1; sum4[2] += x2; sum4[3] += x3;
-            sq4[0] = fmaf(x0, x0, sq4[0]); sq4[1] = fmaf(x1, x1, sq4[1]);
-            sq4[2] = fmaf(x2, x2, sq4[2]); sq4[3] = fmaf(x3, x3, sq4[3]);
-            acc[g * 4 + 0] = __float_as_uint(x0); acc[g * 4 + 1] = __float_as_uint(x1);
-            acc[g * 4 + 2] = __float_as_uint(x2); acc[g * 4 + 3] = __float_as_uint(x3);
-          }
+        for (int g = 0; g < 8; ++g) {
+          const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + g * 4));
+          const uint4 rq = *sw(l_f32, lane, g);
+          const float x0 = __uint_as_float(v[g * 4 + 0]) + bq.x + __uint_as_float(rq.x);
+          const float x1 = __uint_as_float(v[g * 4 + 1]) + bq.y + __uint_as_float(rq.y);
+          const float x2 = __uint_as_float(v[g * 4 + 2]) + bq.z + __uint_as_float(rq.z);
+          const float x3 = __uint_as_float(v[g * 4 + 3]) + bq.w + __uint_as_float(rq.w);
+          sum4[0] += x0; sum4[1] += x1; sum4[2] += x2; sum4[3] += x3;
+          sq4[0] = fmaf(x0, x0, sq4[0]); sq4[1] = fmaf(x1, x1, sq4[1]);
+          sq4[2] = fmaf(x2, x2, sq4[2]); sq4[3] = fmaf(x3, x3, sq4[3]);
+          xs[ci][g * 4 + 0] = x0; xs[ci][g * 4 + 1] = x1; xs[ci][g * 4 + 2] = x2; xs[ci][g * 4 + 3] = x3;
         }
-        tmem_st32(taddr + dc * 64, v);
-        tmem_st32(taddr + dc * 64 + 32, w);
       }
-      tmem_wait_st();
       float tot = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       float tsq = (sq4[0] + sq4[1]) + (sq4[2] + sq4[3]);
-      red[half * 128 + r] = tot;                     // combine the two column halves of every row
-      red[256 + half * 128 + r] = tsq;
-      epi_bar();
-      tot += red[(half ^ 1) * 128 + r];
-      tsq += red[256 + (half ^ 1) * 128 + r];
+      lred[grp * 128 + r] = tot;                     // combine the four column groups of every row
+      lred[512 + grp * 128 + r] = tsq;
+      ln_bar();
+      tot = (lred[r] + lred[128 + r]) + (lred[256 + r] + lred[384 + r]);
+      tsq = (lred[512 + r] + lred[640 + r]) + (lred[768 + r] + lred[896 + r]);
       if (p.ln_cluster) {                            // push this CTA's row statistics into the peer, wait for the peer's
-        if (half == 0) {
+        if (grp == 0) {
           st_cluster_f32(map_to_cta(smem_u32(&xred[r]), peer), tot);
           st_cluster_f32(map_to_cta(smem_u32(&xred[128 + r]), peer), tsq);
           mbar_arrive_cluster(map_to_cta(smem_u32(&xbar[0]), peer));
@@ -465,46 +466,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       const float mean = tot * inv_n;
       const float rstd = rsqrtf(fmaxf(tsq * inv_n - mean * mean, 0.f) + p.ln_eps);
-      // pass C: normalise, gamma/beta, stage, coalesced copy-out
-      for (int dc = half; dc < BLOCK_N / 64; dc += 2) {
-        const int n0 = nbase + dc * 64;
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int n0 = nbase + ci * 128 + grp * 32;
         __syncwarp();
-        tmem_ld32(taddr + dc * 64, v);
-        tmem_ld32(taddr + dc * 64 + 32, w);
-        tmem_wait_ld();
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t* acc = hh ? w : v;
+        for (int g = 0; g < 8; ++g) {
+          const float4 gq = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + n0 + g * 4));
+          const float4 bq = __ldg(reinterpret_cast<const float4*>(p.ln_beta + n0 + g * 4));
+          const float y0 = (xs[ci][g * 4 + 0] - mean) * rstd * gq.x + bq.x;
+          const float y1 = (xs[ci][g * 4 + 1] - mean) * rstd * gq.y + bq.y;
+          const float y2 = (xs[ci][g * 4 + 2] - mean) * rstd * gq.z + bq.z;
+          const float y3 = (xs[ci][g * 4 + 3] - mean) * rstd * gq.w + bq.w;
+          *sw(l_f32, lane, g) = make_uint4(__float_as_uint(y0), __float_as_uint(y1), __float_as_uint(y2), __float_as_uint(y3));
+          xs[ci][g * 4 + 0] = y0; xs[ci][g * 4 + 1] = y1; xs[ci][g * 4 + 2] = y2; xs[ci][g * 4 + 3] = y3;
+        }
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 gq = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + n0 + hh * 32 + g * 4));
-            const float4 bq = __ldg(reinterpret_cast<const float4*>(p.ln_beta + n0 + hh * 32 + g * 4));
-            float y[4];
-            y[0] = (__uint_as_float(acc[g * 4 + 0]) - mean) * rstd * gq.x + bq.x;
-            y[1] = (__uint_as_float(acc[g * 4 + 1]) - mean) * rstd * gq.y + bq.y;
-            y[2] = (__uint_as_float(acc[g * 4 + 2]) - mean) * rstd * gq.z + bq.z;
-            y[3] = (__uint_as_float(acc[g * 4 + 3]) - mean) * rstd * gq.w + bq.w;
-            *sw(s_f32 + hh * 4096, lane, g) = make_uint4(__float_as_uint(y[0]), __float_as_uint(y[1]),
-                                                            __float_as_uint(y[2]), __float_as_uint(y[3]));
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[g * 4 + e] = __float_as_uint(y[e]);
-          }
-          {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 u;
-              u.x = pack_half2(__uint_as_float(acc[g * 8 + 0]), __uint_as_float(acc[g * 8 + 1]));
-              u.y = pack_half2(__uint_as_float(acc[g * 8 + 2]), __uint_as_float(acc[g * 8 + 3]));
-              u.z = pack_half2(__uint_as_float(acc[g * 8 + 4]), __uint_as_float(acc[g * 8 + 5]));
-              u.w = pack_half2(__uint_as_float(acc[g * 8 + 6]), __uint_as_float(acc[g * 8 + 7]));
-              *sw(s_h, lane, hh * 4 + g) = u;
-            }
-          }
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_half2(xs[ci][g * 8 + 0], xs[ci][g * 8 + 1]);
+          u.y = pack_half2(xs[ci][g * 8 + 2], xs[ci][g * 8 + 3]);
+          u.z = pack_half2(xs[ci][g * 8 + 4], xs[ci][g * 8 + 5]);
+          u.w = pack_half2(xs[ci][g * 8 + 6], xs[ci][g * 8 + 7]);
+          *reinterpret_cast<uint4*>(l_h + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = u;
         }
         __syncwarp();
-        store_f32_slab(s_f32, p.out_f32, p.ld_f32, n0, 64);
-        store_f32_slab(s_f32 + 4096, p.out_f32, p.ld_f32, n0 + 32, 32);
-        store_f16_slab(s_h, p.out_h, p.ld_h, n0, 64);
+        store_f32_slab(l_f32, p.out_f32, p.ld_f32, n0, 32);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {               // 8 rows x 64 B per instruction
+          const int row = it * 8 + (lane >> 2), chunk = lane & 3;
+          if (row < rows_here)
+            *reinterpret_cast<uint4*>(p.out_h + (grow0 + row) * p.ld_h + n0 + chunk * 8) =
+                *reinterpret_cast<const uint4*>(l_h + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+        }
       }
     } else if constexpr (MODE == EPI_COUPLING) {
       // columns [0, hN) = log_scale, [hN, 2 hN) = shift, hN = N / 2 = 64 (modules/flow.py:223-257).
@@ -623,7 +617,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
-  if (p.ln_cluster) cluster_sync_all();   // no CTA of the pair exits while the other may still address its shared memory
+  if (p.ln_cluster) cluster_sync_relaxed();   // no CTA of the pair exits while the other may still address its shared memory
 }
 
 }  // namespace vb

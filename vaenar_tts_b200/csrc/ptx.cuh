@@ -71,6 +71,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA in the cluster
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// execution-only rendezvous (no memory ordering): used at kernel exit so that no CTA of the pair leaves while the
+// other may still address its shared memory; avoids the release fence that would wait for all global stores to drain
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
 // shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank`
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
   uint32_t r;

@@ -507,6 +507,23 @@ __global__ void randn_kernel(float* __restrict__ out, long n, uint64_t seed, uin
   for (int j = 0; j < 4 && i4 * 4 + j < n; ++j) out[i4 * 4 + j] = v[j];
 }
 
+// Keras Adam over the FLAT parameter buffer (train.py:116-117, TF 2.2 ResourceApplyAdam form):
+//   lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr_t m / (sqrt(v) + eps)
+// `trainable` is a per-element byte mask (BatchNorm moving statistics and alignment padding are skipped);
+// grad_scale folds the 1/world_size of the data-parallel gradient mean.
+__global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, const uint8_t* __restrict__ trainable, long n, float lr_t, float b1,
+                                 float b2, float eps, float grad_scale) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n || !trainable[i]) return;
+  const float gi = g[i] * grad_scale;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
 // Inverted-dropout keep mask (Keras Dropout): 0 with probability rate, else 1/(1-rate); same Philox stream layout.
 __global__ void dropout_mask_kernel(float* __restrict__ out, long n, float rate, uint64_t seed, uint64_t stream) {
   const long i4 = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;

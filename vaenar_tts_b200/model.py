@@ -186,6 +186,28 @@ class VAENAR:
     def mark_weights_changed(self):
         self._dirty = True
 
+    def apply_gradients(self, flat_grads, step, lr=None, beta_1=0.9, beta_2=0.999, epsilon=1e-7, grad_scale=1.0):
+        """optimizer.apply_gradients of train.py:137 (Keras Adam, lr 1.25e-4) over the flat gradient buffer, which has
+        the layout of the flat parameter buffer.  One fused kernel; Adam moments are created on first use."""
+        self._require_cuda()
+        g = self._f32(flat_grads)
+        if g.numel() != self._flat.numel():
+            raise VaenarError("gradient buffer must have the flat parameter layout")
+        if not hasattr(self, "_adam_m"):
+            self._adam_m = torch.zeros_like(self._flat)
+            self._adam_v = torch.zeros_like(self._flat)
+            host = torch.zeros(self._flat.numel(), dtype=torch.uint8)
+            check(self._lib.vaenar_trainable_mask(self._h, ctypes.c_void_p(host.data_ptr())))
+            self._trainable_mask = host.to(self.device)
+        lr = float(self.hps.Train.learning_rate if lr is None else lr)
+        check(self._lib.vaenar_adam_step(self._p(self._flat), self._p(g), self._p(self._adam_m), self._p(self._adam_v),
+                                         self._p(self._trainable_mask), self._flat.numel(), int(step), lr, float(beta_1),
+                                         float(beta_2), float(epsilon), float(grad_scale), self._stream()))
+        self._dirty = True
+
+    def flat_parameters(self):
+        return self._flat
+
     # ------------------------------------------------------------------ plumbing
     def _require_cuda(self):
         if self.device.type != "cuda":
