@@ -38,6 +38,6 @@ for r in rows:
     k = (tuple(r["grid"]), r["mode"], r["N"], r["K"], r["bn"])
     a = agg[k]
     a[0] += 1; a[1] += (r["end"] - r["start"]) / 1e3; a[2] += r["setup"] / 1e3; a[3] += r["main"] / 1e3; a[4] += r["epi"] / 1e3
-print("grid        mode N    K     bn  | n  span_us  setup  main  epi")
+print("grid        mode N    K     bn  | n  span_us  setup  main  epi   (mode 100/101/102 = self/cross/cross+ali attention: setup, pass1, pass2, epilogue->[3..4])")
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{str(k[0]):11s} {k[1]:4d} {k[2]:4d} {k[3]:5d} {k[4]:4d} | {a[0]:2d} {a[1]/a[0]:7.2f} {a[2]/a[0]:6.2f} {a[3]/a[0]:6.2f} {a[4]/a[0]:6.2f}")

@@ -52,6 +52,7 @@ struct AttnParams {
   __half* ctx;           // [B*Tq, ctx_ld] fp16, head h at columns h*64
   int ctx_ld;
   float* ali;            // optional [B, H, Tq, Tk] fp32
+  unsigned long long* dbg;   // optional per-CTA phase timestamps (tuning aid), 8 x u64 per CTA
 };
 
 template <bool kWriteAli>
@@ -78,6 +79,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
   float* red = reinterpret_cast<float*>(bars + 32);   // [3][2][128] row-statistic exchange between the two column halves
 
+  unsigned long long* dbg = p.dbg ? p.dbg + ((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 64) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[0] = t; }
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * ATT_BQ;
@@ -122,6 +125,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();   // PDL: prologue overlapped the previous kernel's tail
   pdl_wait();
+  if (dbg && threadIdx.x == 64) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[1] = t; dbg[5] = static_cast<unsigned long long>(nblk); }
   const uint32_t tmem_S = tmem_base;          // two buffers: columns [0,128) and [128,256)
   const uint32_t tmem_O = tmem_base + 256;    // columns [256, 320)
 
@@ -267,6 +271,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_before();
       mbar_arrive(&s_empty[st]);
     }
+    if (dbg && threadIdx.x == 64) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[2] = t; }
     // combine the column groups of every row
     red_m[grp * ATT_BQ + r] = m;
     if (kWriteAli) red_l[grp * ATT_BQ + r] = l;
@@ -348,6 +353,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int kk = k_done + grp; kk < p.Tk; kk += ATT_GROUPS) arow[kk] = fill;
     }
 
+    if (dbg && threadIdx.x == 64) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[3] = t; }
     // ---- epilogue: ctx = O / l ; column groups 0 and 1 each write 32 of the 64 head channels
     float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
     red_s[grp * ATT_BQ + r] = lsum;
@@ -382,6 +388,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
     tc_fence_before();
+    if (dbg && threadIdx.x == 64) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[4] = t; }
   }
   __syncthreads();
   if (warp == 1) {

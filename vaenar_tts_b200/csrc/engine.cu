@@ -466,6 +466,7 @@ static bool g_use_pdl = true;   // programmatic dependent launch between the ten
 static unsigned long long* g_dbg_cursor = nullptr;   // tuning aid: per-CTA phase timestamps of GEMM launches
 static unsigned long long* g_dbg_base = nullptr;
 static std::vector<std::string> g_dbg_launches;
+static bool g_dbg_attn = true;
 static bool g_profile = false;
 static std::map<std::string, KernelStat> g_stats;
 static std::string g_profile_json;
@@ -667,6 +668,17 @@ static void run_attention(Ctx& c, int B, int H, const AttnCall& a) {
   p.q_len = a.q_len; p.k_len = a.k_len; p.causal = a.causal;
   p.scale = 1.0f / sqrtf(static_cast<float>(ATT_D));   // attention.py:227-229, temperature 1.0
   p.ctx = a.ctx; p.ctx_ld = a.ctx_ld; p.ali = a.ali;
+  p.dbg = nullptr;
+  if (g_dbg_cursor && g_dbg_attn) {
+    if (g_dbg_launches.empty()) g_dbg_base = g_dbg_cursor;
+    p.dbg = g_dbg_cursor;
+    const unsigned gx = cdiv(a.Tq, ATT_BQ);
+    char buf[256];
+    snprintf(buf, sizeof(buf), "{\"grid\": [%u, %d], \"mode\": %d, \"N\": %d, \"K\": %d, \"bn\": %d, \"offset\": %lld}", gx, H * B,
+             a.causal ? 100 : (a.ali ? 102 : 101), a.Tq, a.Tk, 0, static_cast<long long>(g_dbg_cursor - g_dbg_base));
+    g_dbg_launches.push_back(buf);
+    g_dbg_cursor += static_cast<size_t>(gx) * H * B * 8;
+  }
   const CUtensorMap tQ = make_tmap(a.q, 3, a.q_ld, a.Tq, B, a.q_ld, static_cast<uint64_t>(a.Tq) * a.q_ld, 64, 128);
   const CUtensorMap tK = make_tmap(a.k, 3, a.k_ld, a.Tk, B, a.k_ld, static_cast<uint64_t>(a.Tk) * a.k_ld, 64, 128);
   const CUtensorMap tV = make_tmap(a.vt, 2, a.Tk, a.vt_rows, 1, a.vt_ld, 0, 64, 64);
