@@ -180,6 +180,11 @@ int vaenar_test_attention(const float* q, const float* k, const float* v, const 
                           const int32_t* k_len, int B, int H, int Tq, int Tk, int causal, float* ctx, float* ali,
                           void* ws, int64_t ws_bytes, void* stream);
 
+/* Weight gradient of a Dense / Conv1D layer on tcgen05 with MN-major operands (csrc/wgrad_tc.cuh):
+ * dW[tap][Cin (+Cin2)][Cout] = sum_{b,t} [X ; X2][b, t + tap - (taps-1)/2, :]^T dY[b, t, :]  (fp32 out, fp16 operands). */
+int vaenar_test_wgrad(const float* X, const float* X2, const float* dY, int B, int T, int Cin, int Cin2, int Cout, int taps,
+                      float* dW, void* ws, int64_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

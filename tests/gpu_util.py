@@ -67,3 +67,19 @@ def attention(q, k, v, q_len, k_len, H, causal, want_ali=True):
                                     _p(ws), ws.numel(), _stream()))
     torch.cuda.synchronize()
     return ctx.cpu(), (ali.cpu() if ali is not None else None)
+
+
+def wgrad(X, dY, X2=None, taps=1):
+    """dW[taps, Cin(+Cin2), Cout] of a Dense (taps=1) / Conv1D 'same' layer from X [B,T,Cin], dY [B,T,Cout]."""
+    lib = _lib.load()
+    X, dY = X.cuda().float().contiguous(), dY.cuda().float().contiguous()
+    X2 = X2.cuda().float().contiguous() if X2 is not None else None
+    B, T, Cin = X.shape
+    Cin2 = X2.shape[2] if X2 is not None else 0
+    Cout = dY.shape[2]
+    out = torch.full((taps, Cin + Cin2, Cout), float("nan"), device="cuda")
+    ws = workspace()
+    check(lib.vaenar_test_wgrad(_p(X), _p(X2), _p(dY), B, T, Cin, Cin2, Cout, taps, _p(out), _p(ws), ws.numel(),
+                                _stream()))
+    torch.cuda.synchronize()
+    return out.cpu()

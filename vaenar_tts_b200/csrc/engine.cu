@@ -18,6 +18,7 @@
 #include "attention_tc.cuh"
 #include "gemm_tc.cuh"
 #include "simt_kernels.cuh"
+#include "wgrad_tc.cuh"
 
 using namespace vb;
 
@@ -524,6 +525,7 @@ static void set_attrs(vaenar_model* m) {
 #undef VB_SET_ATTR
   VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+  VB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
   VB_CUDA(cudaFuncSetAttribute(slogdet128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOW_DIM * (FLOW_DIM + 1) * 8));
   VB_CUDA(cudaFuncSetAttribute(inverse128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FLOW_DIM * (2 * FLOW_DIM + 1) + FLOW_DIM) * 4));
   VB_CUDA(cudaFuncSetAttribute(flow_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FLOW_DIM * FLOW_DIM + 32 * FLOW_DIM) * 4));
@@ -648,6 +650,53 @@ static GemmParams gp() {
   memset(&p, 0, sizeof(p));
   p.ln_eps = 1e-3f;   // Keras LayerNormalization default epsilon
   return p;
+}
+
+// ---- weight gradient: dW[M, N] (+)= X^T dY over tokens (csrc/wgrad_tc.cuh).  X / dY are row-major fp16
+// [batches, rows, ld] tensors; `x1` (optional) supplies the dW rows >= a_split (Dense over a concat).
+struct WOp {
+  const __half* p = nullptr;
+  int ld = 0;     // row pitch in elements
+  int C = 0;      // channel extent of the tensor map (columns >= C read as zero)
+  int col0 = 0;   // first channel of the operand window
+};
+static void run_wgrad(Ctx& c, WOp x0, WOp x1, int a_split, WOp dy, int batches, int rows, int shift, int M, int N,
+                      float* out, int ldo) {
+  if (c.dry) return;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.batches = batches; p.rows = rows;
+  p.kb_per_batch = cdiv(rows, WG_BLOCK_K);
+  p.total_kb = batches * p.kb_per_batch;
+  const int tiles = cdiv(M, WG_BLOCK_M) * cdiv(N, WG_BLOCK_N);
+  int splits = std::max(1, std::min(p.total_kb, cdiv(2 * 148, tiles)));   // about two waves of CTAs
+  p.kb_per_split = cdiv(p.total_kb, splits);
+  splits = cdiv(p.total_kb, p.kb_per_split);
+  p.M = M; p.N = N;
+  if (!x1.p) { x1 = x0; a_split = M; }
+  p.a_split = a_split; p.a_shift = shift;
+  p.a0_col0 = x0.col0; p.a1_col0 = x1.col0; p.b_col0 = dy.col0;
+  p.out = out; p.ldo = ldo;
+  if (a_split % WG_BLOCK_M != 0 && a_split != M) VB_THROW("wgrad: concat boundary %d must be a multiple of %d", a_split, WG_BLOCK_M);
+  const CUtensorMap tA0 = make_tmap(x0.p, 3, x0.C, rows, batches, x0.ld, static_cast<uint64_t>(rows) * x0.ld, 64, 64);
+  const CUtensorMap tA1 = make_tmap(x1.p, 3, x1.C, rows, batches, x1.ld, static_cast<uint64_t>(rows) * x1.ld, 64, 64);
+  const CUtensorMap tB = make_tmap(dy.p, 3, dy.C, rows, batches, dy.ld, static_cast<uint64_t>(rows) * dy.ld, 64, 64);
+  const double tokens = static_cast<double>(batches) * rows;
+  ProfileScope prof("wgrad", 2.0 * tokens * M * N, tokens * (M + N) * 2 + static_cast<double>(M) * N * 4, c.stream);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(cdiv(M, WG_BLOCK_M), cdiv(N, WG_BLOCK_N), splits);
+  cfg.blockDim = dim3(WG_THREADS);
+  cfg.dynamicSmemBytes = WG_SMEM;
+  cfg.stream = c.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, wgrad_tc_kernel, tA0, tA1, tB, p);
+  if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(wgrad_tc_kernel) failed: %s", cudaGetErrorString(le));
+  check_launch("wgrad_tc_kernel");
 }
 
 struct AttnCall {
@@ -1867,6 +1916,29 @@ int vaenar_test_attention(const float* q, const float* k, const float* v, const 
   const long nc = static_cast<long>(B) * Tq * D;
   half_to_float_kernel<<<static_cast<unsigned>((nc + 255) / 256), 256, 0, c.stream>>>(ch, ctx, nc);
   check_launch("half_to_float");
+  API_END
+}
+
+/* dW[taps][Cin][Cout] = sum_{b,t} X[b, t + tap - (taps-1)/2, :]^T dY[b, t, :]  (taps = 1: Dense weight gradient).
+ * X [B,T,Cin], dY [B,T,Cout] fp32 (cast to fp16 operands here); X2 (nullable) [B,T,Cin2] supplies rows Cin.. of a
+ * concat-Dense gradient. */
+int vaenar_test_wgrad(const float* X, const float* X2, const float* dY, int B, int T, int Cin, int Cin2, int Cout, int taps,
+                      float* dW, void* ws, int64_t ws_bytes, void* stream) {
+  API_BEGIN
+  TestCtx c;
+  test_ctx(c, ws, ws_bytes, stream);
+  const int64_t tok = static_cast<int64_t>(B) * T;
+  __half* xh = c.alloc<__half>(tok * Cin);
+  __half* x2h = X2 ? c.alloc<__half>(tok * Cin2) : nullptr;
+  __half* dyh = c.alloc<__half>(tok * Cout);
+  run_cast(c, X, xh, tok * Cin);
+  if (X2) run_cast(c, X2, x2h, tok * Cin2);
+  run_cast(c, dY, dyh, tok * Cout);
+  const int M = Cin + (X2 ? Cin2 : 0);
+  VB_CUDA(cudaMemsetAsync(dW, 0, static_cast<int64_t>(taps) * M * Cout * 4, c.stream));
+  for (int j = 0; j < taps; ++j)
+    run_wgrad(c, WOp{xh, Cin, Cin, 0}, X2 ? WOp{x2h, Cin2, Cin2, 0} : WOp{}, Cin, WOp{dyh, Cout, Cout, 0}, B, T,
+              j - (taps - 1) / 2, M, Cout, dW + static_cast<int64_t>(j) * M * Cout, Cout);
   API_END
 }
 
