@@ -185,6 +185,12 @@ int vaenar_test_attention(const float* q, const float* k, const float* v, const 
 int vaenar_test_wgrad(const float* X, const float* X2, const float* dY, int B, int T, int Cin, int Cin2, int Cout, int taps,
                       float* dW, void* ws, int64_t ws_bytes, void* stream);
 
+/* Backward of the attention core (csrc/attention_bwd_tc.cuh; forward recomputed for the softmax statistics):
+ * dq [B,Tq,H*64], dk, dv [B,Tk,H*64] from the context gradient dctx [B,Tq,H*64]. */
+int vaenar_test_attention_bwd(const float* q, const float* k, const float* v, const float* dctx, const int32_t* q_len,
+                              const int32_t* k_len, int B, int H, int Tq, int Tk, int causal, float* dq, float* dk,
+                              float* dv, void* ws, int64_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,3 +83,20 @@ def wgrad(X, dY, X2=None, taps=1):
                                 _stream()))
     torch.cuda.synchronize()
     return out.cpu()
+
+
+def attention_bwd(q, k, v, dctx, q_len, k_len, H, causal):
+    lib = _lib.load()
+    q, k, v, dctx = (t.cuda().float().contiguous() for t in (q, k, v, dctx))
+    B, Tq, _ = q.shape
+    Tk = k.shape[1]
+    ql = q_len.cuda().int().contiguous()
+    kl = k_len.cuda().int().contiguous()
+    dq = torch.full_like(q, float("nan"))
+    dk = torch.full_like(k, float("nan"))
+    dv = torch.full_like(v, float("nan"))
+    ws = workspace()
+    check(lib.vaenar_test_attention_bwd(_p(q), _p(k), _p(v), _p(dctx), _p(ql), _p(kl), B, H, Tq, Tk, int(causal), _p(dq),
+                                        _p(dk), _p(dv), _p(ws), ws.numel(), _stream()))
+    torch.cuda.synchronize()
+    return dq.cpu(), dk.cpu(), dv.cpu()

@@ -70,6 +70,8 @@ _SIGS = {
                                   c_int64, _P]),
     "vaenar_test_conv1d": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
     "vaenar_test_attention": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int64, _P]),
+    "vaenar_test_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P,
+                                          c_int64, _P]),
     "vaenar_test_wgrad": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
 }
 EXPORTS = tuple(_SIGS)

@@ -52,6 +52,7 @@ struct AttnParams {
   __half* ctx;           // [B*Tq, ctx_ld] fp16, head h at columns h*64
   int ctx_ld;
   float* ali;            // optional [B, H, Tq, Tk] fp32
+  float* lse2;           // optional [B, H, Tq] fp32: log2 of the softmax denominator incl. the max (saved for the backward pass)
   unsigned long long* dbg;   // optional per-CTA phase timestamps (tuning aid), 8 x u64 per CTA
 };
 
@@ -370,6 +371,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_wait_ld();
       }
       const float on = row_dead ? 0.f : (kWriteAli ? 1.0f : 1.0f / lsum);
+      if (p.lse2 && grp == 0 && row_store)
+        p.lse2[(static_cast<long>(b) * p.H + h) * p.Tq + q] = row_dead ? 0.f : msl2 + log2f(lsum);
       if (row_store) {
         __half* dst = p.ctx + (static_cast<long>(b) * p.Tq + q) * p.ctx_ld + h * ATT_D + grp * 32;
 #pragma unroll

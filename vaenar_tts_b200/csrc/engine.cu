@@ -16,6 +16,7 @@
 
 #include "../../include/vaenar_b200.h"
 #include "attention_tc.cuh"
+#include "attention_bwd_tc.cuh"
 #include "gemm_tc.cuh"
 #include "simt_kernels.cuh"
 #include "wgrad_tc.cuh"
@@ -525,6 +526,8 @@ static void set_attrs(vaenar_model* m) {
 #undef VB_SET_ATTR
   VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+  VB_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_DKDV_SMEM));
+  VB_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_DQ_SMEM));
   VB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
   VB_CUDA(cudaFuncSetAttribute(slogdet128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOW_DIM * (FLOW_DIM + 1) * 8));
   VB_CUDA(cudaFuncSetAttribute(inverse128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FLOW_DIM * (2 * FLOW_DIM + 1) + FLOW_DIM) * 4));
@@ -707,6 +710,7 @@ struct AttnCall {
   int causal;
   __half* ctx; int ctx_ld;
   float* ali;
+  float* lse2 = nullptr;   // [B, H, Tq] softmax statistic saved for the backward pass (training)
 };
 static void run_attention(Ctx& c, int B, int H, const AttnCall& a) {
   if (c.dry) return;
@@ -716,7 +720,7 @@ static void run_attention(Ctx& c, int B, int H, const AttnCall& a) {
   p.vt = a.vt; p.vt_ld = a.vt_ld;
   p.q_len = a.q_len; p.k_len = a.k_len; p.causal = a.causal;
   p.scale = 1.0f / sqrtf(static_cast<float>(ATT_D));   // attention.py:227-229, temperature 1.0
-  p.ctx = a.ctx; p.ctx_ld = a.ctx_ld; p.ali = a.ali;
+  p.ctx = a.ctx; p.ctx_ld = a.ctx_ld; p.ali = a.ali; p.lse2 = a.lse2;
   p.dbg = nullptr;
   if (g_dbg_cursor && g_dbg_attn) {
     if (g_dbg_launches.empty()) g_dbg_base = g_dbg_cursor;
@@ -750,6 +754,72 @@ static void run_attention(Ctx& c, int B, int H, const AttnCall& a) {
                                : cudaLaunchKernelEx(&cfg, attention_tc_kernel<false>, tQ, tK, tV, p);
   if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(attention_tc_kernel) failed: %s", cudaGetErrorString(le));
   check_launch("attention_tc_kernel");
+}
+
+// ---- attention backward (csrc/attention_bwd_tc.cuh).  All tensors row-major fp16 [B*T, ld]; head h at col0 + h*64.
+struct AttnBwdCall {
+  const __half* q; int q_ld, q_col0; int Tq;
+  const __half* k; int k_ld, k_col0; int Tk;
+  const __half* v; int v_ld, v_col0;
+  const __half* o; int o_ld;                 // forward context [B*Tq, H*64]
+  const __half* dO; int do_ld, do_col0;
+  const int* q_len; const int* k_len; int causal;
+  const float* lse2;
+  float* delta;                              // scratch [B, H, Tq]
+  __half* dq; int dq_ld, dq_col0;
+  __half* dk; int dk_ld, dk_col0;
+  __half* dv; int dv_ld, dv_col0;
+};
+static void run_attention_bwd(Ctx& c, int B, int H, const AttnBwdCall& a) {
+  if (c.dry) return;
+  {
+    const long rows = static_cast<long>(B) * a.Tq;
+    attn_delta_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, c.stream>>>(a.dO, a.do_ld, a.do_col0, a.o, a.o_ld, a.delta,
+                                                                                B, a.Tq, H);
+    check_launch("attn_delta");
+  }
+  AttnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.H = H; p.Tq = a.Tq; p.Tk = a.Tk;
+  p.q_col0 = a.q_col0; p.k_col0 = a.k_col0; p.v_col0 = a.v_col0; p.do_col0 = a.do_col0;
+  p.q_len = a.q_len; p.k_len = a.k_len; p.causal = a.causal;
+  p.scale = 1.0f / sqrtf(static_cast<float>(ATT_D));
+  p.lse2 = a.lse2; p.delta = a.delta;
+  p.dq = a.dq; p.dq_ld = a.dq_ld; p.dq_col0 = a.dq_col0;
+  p.dk = a.dk; p.dk_ld = a.dk_ld; p.dk_col0 = a.dk_col0;
+  p.dv = a.dv; p.dv_ld = a.dv_ld; p.dv_col0 = a.dv_col0;
+  const CUtensorMap tQ = make_tmap(a.q, 3, a.q_ld, a.Tq, B, a.q_ld, static_cast<uint64_t>(a.Tq) * a.q_ld, 64, 128);
+  const CUtensorMap tK = make_tmap(a.k, 3, a.k_ld, a.Tk, B, a.k_ld, static_cast<uint64_t>(a.Tk) * a.k_ld, 64, 128);
+  const CUtensorMap tV = make_tmap(a.v, 3, a.v_ld, a.Tk, B, a.v_ld, static_cast<uint64_t>(a.Tk) * a.v_ld, 64, 128);
+  const CUtensorMap tO = make_tmap(a.dO, 3, a.do_ld, a.Tq, B, a.do_ld, static_cast<uint64_t>(a.Tq) * a.do_ld, 64, 128);
+  const double work = static_cast<double>(B) * H * a.Tq * a.Tk;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(ATB_THREADS);
+  cfg.stream = c.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  {
+    ProfileScope prof(a.causal ? "attn_bwd_dkdv_self" : "attn_bwd_dkdv_cross", 8.0 * work * ATT_D,
+                      static_cast<double>(B) * H * ATT_D * 2 * (2.0 * a.Tq + 4.0 * a.Tk), c.stream);
+    cfg.gridDim = dim3(cdiv(a.Tk, 128), H, B);
+    cfg.dynamicSmemBytes = ATB_DKDV_SMEM;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, attn_bwd_dkdv_kernel, tQ, tK, tV, tO, p);
+    if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(attn_bwd_dkdv_kernel) failed: %s", cudaGetErrorString(le));
+    check_launch("attn_bwd_dkdv_kernel");
+  }
+  {
+    ProfileScope prof(a.causal ? "attn_bwd_dq_self" : "attn_bwd_dq_cross", 6.0 * work * ATT_D,
+                      static_cast<double>(B) * H * ATT_D * 2 * (3.0 * a.Tq + 2.0 * a.Tk), c.stream);
+    cfg.gridDim = dim3(cdiv(a.Tq, 128), H, B);
+    cfg.dynamicSmemBytes = ATB_DQ_SMEM;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, attn_bwd_dq_kernel, tQ, tK, tV, tO, p);
+    if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(attn_bwd_dq_kernel) failed: %s", cudaGetErrorString(le));
+    check_launch("attn_bwd_dq_kernel");
+  }
 }
 
 static void run_cast(Ctx& c, const float* in, __half* out, int64_t n) {
@@ -1939,6 +2009,48 @@ int vaenar_test_wgrad(const float* X, const float* X2, const float* dY, int B, i
   for (int j = 0; j < taps; ++j)
     run_wgrad(c, WOp{xh, Cin, Cin, 0}, X2 ? WOp{x2h, Cin2, Cin2, 0} : WOp{}, Cin, WOp{dyh, Cout, Cout, 0}, B, T,
               j - (taps - 1) / 2, M, Cout, dW + static_cast<int64_t>(j) * M * Cout, Cout);
+  API_END
+}
+
+/* Backward of the attention core: q,k,v,dctx fp32 [B,T,H*64] -> dq,dk,dv fp32 (computed on fp16 operands). */
+int vaenar_test_attention_bwd(const float* q, const float* k, const float* v, const float* dctx, const int32_t* q_len,
+                              const int32_t* k_len, int B, int H, int Tq, int Tk, int causal, float* dq, float* dk,
+                              float* dv, void* ws, int64_t ws_bytes, void* stream) {
+  API_BEGIN
+  TestCtx c;
+  test_ctx(c, ws, ws_bytes, stream);
+  const int D = H * 64, tpad = vt_pad(Tk);
+  const int64_t nq = static_cast<int64_t>(B) * Tq * D, nk = static_cast<int64_t>(B) * Tk * D;
+  __half* qh = c.alloc<__half>(nq);
+  __half* kh = c.alloc<__half>(nk);
+  __half* vh = c.alloc<__half>(nk);
+  __half* doh = c.alloc<__half>(nq);
+  __half* vt = c.alloc<__half>(static_cast<int64_t>(B) * D * tpad);
+  __half* ch = c.alloc<__half>(nq);
+  float* lse2 = c.alloc<float>(static_cast<int64_t>(B) * H * Tq);
+  float* delta = c.alloc<float>(static_cast<int64_t>(B) * H * Tq);
+  __half* dqh = c.alloc<__half>(nq);
+  __half* dkh = c.alloc<__half>(nk);
+  __half* dvh = c.alloc<__half>(nk);
+  run_cast(c, q, qh, nq);
+  run_cast(c, k, kh, nk);
+  run_cast(c, v, vh, nk);
+  run_cast(c, dctx, doh, nq);
+  VB_CUDA(cudaMemsetAsync(vt, 0, static_cast<int64_t>(B) * D * tpad * 2, c.stream));
+  vt_transpose_kernel<<<static_cast<unsigned>((nk + 255) / 256), 256, 0, c.stream>>>(v, vt, B, Tk, H, tpad);
+  check_launch("vt_transpose");
+  AttnCall f{qh, D, 0, Tq, kh, D, 0, Tk, vt, static_cast<long>(B) * D, tpad, 0, q_len, k_len, causal, ch, D, nullptr};
+  f.lse2 = lse2;
+  run_attention(c, B, H, f);
+  VB_CUDA(cudaMemsetAsync(dqh, 0xFF, nq * 2, c.stream));   // NaN fill: every element must be written
+  VB_CUDA(cudaMemsetAsync(dkh, 0xFF, nk * 2, c.stream));
+  VB_CUDA(cudaMemsetAsync(dvh, 0xFF, nk * 2, c.stream));
+  run_attention_bwd(c, B, H, AttnBwdCall{qh, D, 0, Tq, kh, D, 0, Tk, vh, D, 0, ch, D, doh, D, 0, q_len, k_len, causal, lse2,
+                                         delta, dqh, D, 0, dkh, D, 0, dvh, D, 0});
+  half_to_float_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, c.stream>>>(dqh, dq, nq);
+  half_to_float_kernel<<<static_cast<unsigned>((nk + 255) / 256), 256, 0, c.stream>>>(dkh, dk, nk);
+  half_to_float_kernel<<<static_cast<unsigned>((nk + 255) / 256), 256, 0, c.stream>>>(dvh, dv, nk);
+  check_launch("half_to_float");
   API_END
 }
 
