@@ -128,8 +128,8 @@ int vaenar_elbo_fwd(vaenar_handle_t h, const float* params, const void* packed, 
 
 /* VAENAR.call forward with training=True semantics (models/models.py:105-197 as called by train.py:129-134):
  * BatchNorm uses batch statistics over (batch, time) incl. padding and updates its moving averages in `params`,
- * dropout is active (encoder, posterior prenet/positional, postnet).  Forward only: the backward pass is not part of
- * this ABI yet. */
+ * dropout is active (encoder, posterior prenet/positional, postnet).  Forward only (dev-style evaluation of the
+ * training-mode arithmetic); the gradients come from vaenar_train_step_grads. */
 int vaenar_elbo_fwd_train(vaenar_handle_t h, float* params, const void* packed, void* ws, int64_t ws_bytes,
                           const int32_t* texts, const float* mels, const int32_t* mel_lengths,
                           const int32_t* text_lengths, const int32_t* z_lengths, const float* eps, int B, int T_text,
@@ -144,10 +144,24 @@ int vaenar_init(vaenar_handle_t h, float* params, void* packed, void* ws, int64_
                 const int32_t* text_lengths, const int32_t* z_lengths, int B, int T_text, int T_z,
                 const vaenar_train_opts_t* opts, float* z_io, float* mel, void* stream);
 
+/* train_step of train.py:120-138 up to the gradients: VAENAR.call(training=True) forward that records what the
+ * backward pass needs, the losses (losses[4] = {total, mel_l2, kl, length_l2}, total = mel_l2 + kl_weight * max(kl, 0) +
+ * length_weight * length_l2, train.py:135) and the hand-written backward pass.  `grads` (flat parameter layout, fully
+ * overwritten) receives loss_scale * dTotal/dparams: all activation gradients are carried multiplied by loss_scale so
+ * that their fp16 tensor-core operand copies stay in range; pass 1/loss_scale (x 1/world_size) as grad_scale to
+ * vaenar_adam_step.  BatchNorm moving averages are updated in `params` (opts->update_bn_stats).  mel_out (nullable):
+ * decoded mel [B, T_mel, 80].  Workspace: vaenar_train_workspace_bytes (holds every saved activation). */
+int64_t vaenar_train_workspace_bytes(vaenar_handle_t h, int B, int T_text, int T_z, int rf);
+int vaenar_train_step_grads(vaenar_handle_t h, float* params, const void* packed, void* ws, int64_t ws_bytes,
+                            const int32_t* texts, const float* mels, const int32_t* mel_lengths, const int32_t* text_lengths,
+                            const int32_t* z_lengths, const float* eps, int B, int T_text, int T_mel, int T_z, int rf,
+                            const vaenar_train_opts_t* opts, float kl_weight, float length_weight, float loss_scale, float* grads,
+                            float* losses, float* mel_out, void* stream);
+
 /* Optimiser half of train_step (train.py:116-117,137): Keras Adam over the flat parameter buffer, one fused launch.
  * `trainable_mask` (device, one byte per float; host copy from vaenar_trainable_mask) skips the BatchNorm moving
  * statistics and padding; grad_scale folds the 1/world_size of the data-parallel gradient mean.  The gradients
- * themselves (backward pass) are not produced by this library yet. */
+ * come from vaenar_train_step_grads. */
 int vaenar_trainable_mask(vaenar_handle_t h, uint8_t* host_mask);
 int vaenar_adam_step(float* params, const float* grads, float* m, float* v, const uint8_t* trainable_mask, int64_t n,
                      int64_t step, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);

@@ -58,6 +58,9 @@ _SIGS = {
     "vaenar_elbo_fwd_train": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                       POINTER(TrainOpts), _P, _P, _P, _P, _P, _P]),
     "vaenar_init": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, POINTER(TrainOpts), _P, _P, _P]),
+    "vaenar_train_workspace_bytes": (c_int64, [_P, c_int, c_int, c_int, c_int]),
+    "vaenar_train_step_grads": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                        POINTER(TrainOpts), c_float, c_float, c_float, _P, _P, _P, _P]),
     "vaenar_trainable_mask": (c_int, [_P, _P]),
     "vaenar_adam_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_float, c_float, c_float, c_float, c_float, _P]),
     "vaenar_randn": (c_int, [_P, c_int64, c_uint64, c_uint64, c_float, _P]),

@@ -20,6 +20,7 @@
 #include "gemm_tc.cuh"
 #include "simt_kernels.cuh"
 #include "wgrad_tc.cuh"
+#include "bwd_kernels.cuh"
 
 using namespace vb;
 
@@ -121,6 +122,7 @@ struct vaenar_model {
   int64_t off_Mf = 0, off_cf = 0, off_Mb = 0, off_cb = 0, off_consts = 0;
   std::vector<PackOp> host_ops;
   std::vector<const float*> host_ptrs;
+  std::vector<float*> host_gptrs;   // flow parameter-gradient pointers (train step)
   bool attrs_set = false;
   cudaStream_t side_stream = nullptr;   // second launch chain for batch-split inference (fork/join with events)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -234,6 +236,36 @@ static void plan_conv(vaenar_model& m, const std::string& pk, const std::string&
                (split && p == 2) ? 1 : 0);
   m.add_vec(pk + ".bn_scale", cout);
   m.add_vec(pk + ".bn_shift", cout);
+}
+
+// ---- backward-pass (dgrad) operands: the Keras [in, out] layout itself as fp16 = [N_gemm = in, K_gemm = out] K-major
+static void plan_bw(vaenar_model& m, const std::string& pk, const std::string& param, int in, int out) {
+  m.add_mat(pk, in, out);
+  m.add_op(pk, 0, 0, param, 0, in, out, out, 2);
+}
+static void plan_bw_xblk(vaenar_model& m, const std::string& pk, const std::string& n, int d, int ffn) {
+  m.add_mat("bw." + pk + ".qkv", d, 3 * d);
+  int i = 0;
+  for (const char* q : {"query", "key", "value"})
+    m.add_op("bw." + pk + ".qkv", 0, (i++) * d, n + ".self_attention." + q + "_layer.kernel", 0, d, d, d, 2);
+  plan_bw(m, "bw." + pk + ".proj1", n + ".att_proj1.kernel", 2 * d, d);
+  plan_bw(m, "bw." + pk + ".cq", n + ".cross_attention.query_layer.kernel", d, d);
+  plan_bw(m, "bw." + pk + ".proj2", n + ".att_proj2.kernel", 2 * d, d);
+  plan_bw(m, "bw." + pk + ".ffn1", n + ".ffn.dense1.kernel", d, ffn);
+  plan_bw(m, "bw." + pk + ".ffn2", n + ".ffn.dense2.kernel", ffn, d);
+}
+static void plan_bw_memkv(vaenar_model& m, const std::string& pk, const std::vector<std::string>& blks, int mem, int d) {
+  const int nb = static_cast<int>(blks.size());
+  m.add_mat(pk, mem, 2 * nb * d);
+  for (int i = 0; i < nb; ++i) {
+    m.add_op(pk, 0, i * d, blks[i] + ".cross_attention.key_layer.kernel", 0, mem, d, d, 2);
+    m.add_op(pk, 0, nb * d + i * d, blks[i] + ".cross_attention.value_layer.kernel", 0, mem, d, d, 2);
+  }
+}
+static void plan_bw_conv(vaenar_model& m, const std::string& pk, const std::string& n, int k, int cin, int cout) {
+  m.add_mat(pk, cin, k * cout);
+  for (int j = 0; j < k; ++j)
+    m.add_op(pk, 0, j * cout, n + ".conv1d.kernel", static_cast<int64_t>(j) * cin * cout, cin, cout, cout, 2);
 }
 
 static void build_model(vaenar_model& m) {
@@ -391,6 +423,67 @@ static void build_model(vaenar_model& m) {
   m.add_mat("dec.res", O, 3 * h.post_filters);
   for (int p = 0; p < 3; ++p)
     m.add_op("dec.res", 0, p * h.post_filters, "decoder.residual_projection.kernel", 0, h.post_filters, O, O, p == 2 ? 1 : 0);
+  // ---- backward-pass operands (training only; same arena)
+  {
+    int cin = h.embd_dim;
+    for (int i = 0; i < h.enc_n_conv; ++i) {
+      plan_bw_conv(m, "bw.enc.conv" + std::to_string(i), "text_encoder.prenet.conv_stack." + std::to_string(i),
+                   h.enc_conv_kernel, cin, E);
+      cin = E;
+    }
+    plan_bw(m, "bw.enc.proj", "text_encoder.prenet.projection.kernel", E, E);
+    for (int i = 0; i < h.enc_n_blk; ++i) {
+      const std::string n = "text_encoder.self_attentions." + std::to_string(i), pk = "bw.enc.blk" + std::to_string(i);
+      const int A = h.enc_att_dim;
+      m.add_mat(pk + ".qkv", E, 3 * A);
+      int c = 0;
+      for (const char* q : {"query", "key", "value"})
+        m.add_op(pk + ".qkv", 0, (c++) * A, n + ".attention." + q + "_layer.kernel", 0, E, A, A, 2);
+      plan_bw(m, pk + ".proj", n + ".att_proj.kernel", E + A, E);
+      plan_bw(m, pk + ".ffn1", n + ".ffn.dense1.kernel", E, h.enc_ffn);
+      plan_bw(m, pk + ".ffn2", n + ".ffn.dense2.kernel", h.enc_ffn, E);
+    }
+    plan_bw(m, "bw.post.pre2", "posterior.prenet.dense2.kernel", h.posterior_pre_hidden, h.posterior_pre_hidden);
+    std::vector<std::string> blks;
+    for (int i = 0; i < h.posterior_nblk; ++i) {
+      const std::string n = "posterior.attentions." + std::to_string(i);
+      plan_bw_xblk(m, "post.blk" + std::to_string(i), n, h.posterior_att_dim, h.posterior_ffn);
+      blks.push_back(n);
+    }
+    plan_bw_memkv(m, "bw.post.kv", blks, E, h.posterior_att_dim);
+    m.add_mat("bw.post.out", h.posterior_att_dim, 2 * L);
+    m.add_op("bw.post.out", 0, 0, "posterior.mu_projection.kernel", 0, h.posterior_att_dim, L, L, 2);
+    m.add_op("bw.post.out", 0, L, "posterior.logvar_projection.kernel", 0, h.posterior_att_dim, L, L, 2);
+    blks.clear();
+    for (int s = 0; s < h.prior_n_blk; ++s) {
+      const std::string n = "prior.glow." + std::to_string(s) + ".affine_coupling.net", pk = "prior." + std::to_string(s);
+      plan_bw(m, "bw." + pk + ".pre", n + ".pre_projection.kernel", L / 2, h.prior_att_dim);
+      for (int j = 0; j < h.prior_n_tblk; ++j) {
+        plan_bw_xblk(m, pk + ".blk" + std::to_string(j), n + ".attentions." + std::to_string(j), h.prior_att_dim, h.prior_ffn);
+        blks.push_back(n + ".attentions." + std::to_string(j));
+      }
+      m.add_mat("bw." + pk + ".out", h.prior_att_dim, L);
+      m.add_op("bw." + pk + ".out", 0, 0, n + ".log_scale_proj.kernel", 0, h.prior_att_dim, L / 2, L / 2, 2);
+      m.add_op("bw." + pk + ".out", 0, L / 2, n + ".shift_proj.kernel", 0, h.prior_att_dim, L / 2, L / 2, 2);
+    }
+    plan_bw_memkv(m, "bw.prior.kv", blks, E, h.prior_att_dim);
+    plan_bw(m, "bw.dec.pre", "decoder.pre_projection.kernel", L, h.dec_att_dim);
+    blks.clear();
+    for (int i = 0; i < h.dec_nblk; ++i) {
+      const std::string n = "decoder.attentions." + std::to_string(i);
+      plan_bw_xblk(m, "dec.blk" + std::to_string(i), n, h.dec_att_dim, h.dec_ffn);
+      blks.push_back(n);
+    }
+    plan_bw_memkv(m, "bw.dec.kv", blks, E, h.dec_att_dim);
+    plan_bw(m, "bw.dec.out", "decoder.out_projection.kernel", h.dec_att_dim, O * h.max_reduction_factor);
+    cin = O;
+    for (int i = 0; i < h.post_n_conv; ++i) {
+      plan_bw_conv(m, "bw.dec.post" + std::to_string(i), "decoder.postnet.conv_stack." + std::to_string(i), h.post_kernel, cin,
+                   h.post_filters);
+      cin = h.post_filters;
+    }
+    plan_bw(m, "bw.dec.res", "decoder.residual_projection.kernel", h.post_filters, O);
+  }
   // flow constants
   const int S = h.prior_n_blk;
   auto region = [&](int64_t bytes) {
@@ -528,6 +621,8 @@ static void set_attrs(vaenar_model* m) {
   VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_DKDV_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_DQ_SMEM));
+  VB_CUDA(cudaFuncSetAttribute(flow_param_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (2 * FLOW_DIM * (FLOW_DIM + 1) + FLOW_DIM) * 4));
   VB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
   VB_CUDA(cudaFuncSetAttribute(slogdet128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOW_DIM * (FLOW_DIM + 1) * 8));
   VB_CUDA(cudaFuncSetAttribute(inverse128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FLOW_DIM * (2 * FLOW_DIM + 1) + FLOW_DIM) * 4));
@@ -569,12 +664,13 @@ static void segs_conv(GemmParams& p, int taps, int cin, bool split) {
 }
 
 // A operands: [batches, rows, K]; W: packed [Nrows, Ktot]; output tile selection by block_n.
+// W: [Nrows, Ktot] K-major with row pitch w_ld (0: Ktot); a K extent that is not a multiple of 64 is zero-filled by TMA.
 static void run_gemm(Ctx& c, int block_n, AOp a0, AOp a1, int batches, int rows, const __half* W, int Ktot, int Nrows,
-                     GemmParams p) {
+                     GemmParams p, int w_ld = 0) {
   if (c.dry) return;
   int tk = 0;
   for (int s = 0; s < p.nseg; ++s) tk += p.seg_kblocks[s];
-  if (tk * 64 != Ktot) VB_THROW("gemm: segments cover %d of K %d", tk * 64, Ktot);
+  if (tk * 64 < Ktot || tk * 64 - Ktot >= 64) VB_THROW("gemm: segments cover %d of K %d", tk * 64, Ktot);
   if (p.mode == EPI_LN && !(p.bias && p.residual && p.out_f32 && p.out_h && p.ln_gamma && p.ln_beta))
     VB_THROW("gemm: the LayerNorm epilogue needs bias, residual, gamma, beta and both outputs");
   // LayerNorm over N = 2 * BLOCK_N: split the columns over a 2-CTA cluster (row statistics via DSMEM)
@@ -589,7 +685,7 @@ static void run_gemm(Ctx& c, int block_n, AOp a0, AOp a1, int batches, int rows,
   if (!a1.p) a1 = a0;
   const CUtensorMap tA0 = make_tmap(a0.p, 3, a0.K, rows, batches, a0.ld, static_cast<uint64_t>(rows) * a0.ld, 64, 128);
   const CUtensorMap tA1 = make_tmap(a1.p, 3, a1.K, rows, batches, a1.ld, static_cast<uint64_t>(rows) * a1.ld, 64, 128);
-  const CUtensorMap tB = make_tmap(W, 2, Ktot, Nrows, 1, Ktot, 0, 64, block_n > 256 ? 256 : block_n);
+  const CUtensorMap tB = make_tmap(W, 2, Ktot, Nrows, 1, w_ld > 0 ? w_ld : Ktot, 0, 64, block_n > 256 ? 256 : block_n);
   dim3 grid(batches * p.tiles_per_batch, cdiv(p.N, block_n));
   const double Mrows = static_cast<double>(batches) * rows;
   const double kalg = p.alg_k > 0 ? p.alg_k : Ktot;   // algorithmic K: no padding, no split-fp16 triple
@@ -859,11 +955,12 @@ static void run_dropout(Ctx& c, const float* x, const float* mask, float* out_f3
 // x = (x * mask2 + pw * table[t]) * mask3 -> fp32 + fp16  (posterior prenet tail in training mode, posterior.py:117-121)
 __global__ void prenet_tail_kernel(float* x, const float* __restrict__ mask2, const float* __restrict__ table,
                                    const float* __restrict__ pw, const float* __restrict__ mask3, int seq_T, int C,
-                                   __half* __restrict__ out_h, long n) {
+                                   __half* __restrict__ out_h, long n, __half* __restrict__ pre_h = nullptr) {
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long row = i / C;
   const int c = static_cast<int>(i % C), t = static_cast<int>(row % seq_T);
+  if (pre_h) pre_h[i] = __float2half_rn(x[i]);   // post-ReLU, pre-dropout value: sign needed by the backward pass
   const float v = (x[i] * mask2[i] + pw[0] * table[static_cast<long>(t) * C + c]) * mask3[i];
   x[i] = v;
   out_h[i] = __float2half_rn(v);
@@ -1138,7 +1235,7 @@ static void coupling_step(Ctx& c, int s, bool backward, float* z, __half* zh, fl
 static void flow_linear(Ctx& c, float* z, __half* zh, const float* M, const float* cvec, int64_t rows) {
   if (c.dry) return;
   flow_linear_kernel<<<static_cast<unsigned>((rows + 31) / 32), 256, (FLOW_DIM * FLOW_DIM + 32 * FLOW_DIM) * 4, c.stream>>>(
-      z, zh, M, cvec, rows);
+      z, z, zh, M, cvec, rows, 0);
   check_launch("flow_linear");
 }
 
@@ -1515,6 +1612,8 @@ static void init_fwd(Ctx& c, const int* texts, const int* t_len, const int* z_le
   c.ws_off = mark;
 }
 
+#include "train.inc"
+
 // ============================================================================ weight packing
 static void pack_weights(vaenar_model* m, const float* params, uint8_t* packed, cudaStream_t stream) {
   const vaenar_hparams_t& h = m->hp;
@@ -1528,7 +1627,8 @@ static void pack_weights(vaenar_model* m, const float* params, uint8_t* packed, 
     op.src = params + m->params[o.param].offset + o.src_off;
     op.dst = reinterpret_cast<__half*>(packed + pm.off) + static_cast<int64_t>(o.n_off) * pm.K + o.k_off;
     op.K = o.K; op.N = o.N; op.lds = o.lds; op.ldd = pm.K; op.mode = o.mode;
-    if (o.n_off + o.N > pm.N || o.k_off + o.K > pm.K) VB_THROW("pack op outside %s", o.dst.c_str());
+    if (o.mode == 2 ? (o.n_off + o.K > pm.N || o.k_off + o.N > pm.K) : (o.n_off + o.N > pm.N || o.k_off + o.K > pm.K))
+      VB_THROW("pack op outside %s", o.dst.c_str());
     m->host_ops.push_back(op);
     maxK = std::max(maxK, o.K);
     maxN = std::max(maxN, o.N);
@@ -1781,6 +1881,35 @@ int vaenar_init(vaenar_handle_t h, float* params, void* packed, void* ws, int64_
   Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
   apply_train_opts(c, params, opts);
   init_fwd(c, texts, text_lengths, z_lengths, B, T_text, T_z, z_io, mel);
+  API_END
+}
+
+int64_t vaenar_train_workspace_bytes(vaenar_handle_t h, int B, int T_text, int T_z, int rf) {
+  try {
+    Ctx c;
+    c.m = h; c.params = nullptr; c.packed = nullptr; c.ws = nullptr; c.ws_bytes = 0; c.dry = true; c.stream = nullptr;
+    c.training = true;
+    train_grads(c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, B, T_text, T_z * rf, T_z, rf, 0.f, 0.f, 1.f, nullptr,
+                nullptr);
+    return align_up(c.ws_peak, 1024) + 4096;
+  } catch (const EngineError& e) {
+    g_err = e.msg;
+    return -1;
+  }
+}
+
+int vaenar_train_step_grads(vaenar_handle_t h, float* params, const void* packed, void* ws, int64_t ws_bytes,
+                            const int32_t* texts, const float* mels, const int32_t* mel_lengths, const int32_t* text_lengths,
+                            const int32_t* z_lengths, const float* eps, int B, int T_text, int T_mel, int T_z, int rf,
+                            const vaenar_train_opts_t* opts, float kl_weight, float length_weight, float loss_scale, float* grads,
+                            float* losses, float* mel_out, void* stream) {
+  API_BEGIN
+  if (!grads || !losses) VB_THROW("null gradient / loss buffer");
+  if (!(loss_scale > 0.f)) VB_THROW("loss_scale must be positive");
+  Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
+  apply_train_opts(c, params, opts);
+  train_grads(c, grads, texts, mels, mel_lengths, text_lengths, z_lengths, eps, B, T_text, T_mel, T_z, rf, kl_weight, length_weight,
+              loss_scale, losses, mel_out);
   API_END
 }
 

@@ -88,6 +88,11 @@ struct GemmParams {
   float* row_acc;                // [M] per-row accumulator (log-det / log q), accumulated (+=)
   const int* lengths;            // [seq_B]
   const float* eps_in;           // EPI_POSTERIOR noise [M, z_ld]
+  // ---- training: tensors saved for the backward pass (all optional)
+  float* ln_rstd;                // EPI_LN: [M] reciprocal standard deviation of every row
+  int v_rowmajor;                // EPI_QKV: the V columns are ALSO written row-major into out_h (next to V^T)
+  float* save_scale;             // EPI_COUPLING: [M, N/2] sigmoid(log_scale + 2)
+  float* save_lv;                // EPI_POSTERIOR: [M, N/2] log-variance
 };
 
 template <int BLOCK_N>
@@ -333,7 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               dst[static_cast<long>(32 + j) * p.vt_ld] = __float2half_rn(__uint_as_float(w[j]));
             }
           }
-          continue;
+          if (!p.v_rowmajor) continue;
         }
         __syncwarp();   // residual slab visible
         const float tscale = f_table ? __ldg(p.add_scale) : 0.f;
@@ -466,6 +471,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       const float mean = tot * inv_n;
       const float rstd = rsqrtf(fmaxf(tsq * inv_n - mean * mean, 0.f) + p.ln_eps);
+      if (p.ln_rstd && grp == 0 && n_tile == 0 && row_ok) p.ln_rstd[grow] = rstd;
 #pragma unroll
       for (int ci = 0; ci < NCH; ++ci) {
         const int n0 = nbase + ci * 128 + grp * 32;
@@ -530,7 +536,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           o[e] = p.backward ? __fdividef(zp[e] - sh, scale + 1e-12f) : scale * zp[e] + sh;
           ld4[e] += __logf(scale);
           v[g * 4 + e] = __float_as_uint(o[e]);
+          w[g * 4 + e] = __float_as_uint(scale);
         }
+        if (p.save_scale && row_ok)
+          *reinterpret_cast<uint4*>(p.save_scale + grow * hN + ch0 + g * 4) = make_uint4(w[g * 4], w[g * 4 + 1], w[g * 4 + 2], w[g * 4 + 3]);
         *sw(s_f32, lane, g) = make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]),
                                          __float_as_uint(o[3]));
       }
@@ -583,7 +592,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             o[e] = ee[e] * expf(0.5f * lv) + mu;
             a4[e] += lv + ee[e] * ee[e];
             v[g * 4 + e] = __float_as_uint(o[e]);
+            w[g * 4 + e] = __float_as_uint(lv);
           }
+          if (p.save_lv && row_ok)
+            *reinterpret_cast<uint4*>(p.save_lv + grow * L + ch0 + g * 4) = make_uint4(w[g * 4], w[g * 4 + 1], w[g * 4 + 2], w[g * 4 + 3]);
           *sw(s_f32, lane, g) = make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]),
                                            __float_as_uint(o[3]));
         }

@@ -10,6 +10,8 @@ namespace vb {
 // ------------------------------------------------------------------ weight packing
 // dst[n * ldd + k] = fp16( src[k * lds + n] )          (mode 0: hi part)
 //                  = fp16( src - float(fp16(src)) )    (mode 1: lo part of the split-fp16 pair)
+// dst[k * ldd + n] = fp16( src[k * lds + n] )          (mode 2: straight copy -- the backward pass (dgrad) wants the
+//                                                       Keras layout itself: [in, out] = [N_gemm, K_gemm] K-major)
 // Keras Dense kernels are [in, out]; the UMMA B operand wants [out, in] (K-major).
 struct PackOp {
   const float* src;
@@ -26,6 +28,13 @@ __global__ void pack_weights_kernel(const PackOp* __restrict__ ops) {
     tile[i][threadIdx.x] = (k < op.K && n < op.N) ? op.src[static_cast<long>(k) * op.lds + n] : 0.f;
   }
   __syncthreads();
+  if (op.mode == 2) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int k = k0 + i, n = n0 + threadIdx.x;
+      if (k < op.K && n < op.N) op.dst[static_cast<long>(k) * op.ldd + n] = __float2half_rn(tile[i][threadIdx.x]);
+    }
+    return;
+  }
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int n = n0 + i, k = k0 + threadIdx.x;
     if (n < op.N && k < op.K) {
@@ -266,18 +275,22 @@ __global__ void flow_fold_kernel(const float* const* __restrict__ Ws, const floa
 // the flow state z carries the log-density).  In place is safe: a CTA stages its 32 rows first.
 // Also emits the fp16 copy consumed by the conditioner's pre-projection GEMM.
 __global__ void __launch_bounds__(256)
-flow_linear_kernel(float* __restrict__ z, __half* __restrict__ z_h, const float* __restrict__ M,
-                   const float* __restrict__ c, long rows) {
+flow_linear_kernel(const float* z_in, float* z, __half* __restrict__ z_h, const float* __restrict__ M,
+                   const float* __restrict__ c, long rows, int transpose) {
   extern __shared__ float smf[];
   float* Ms = smf;                         // [128][128]
   float* Xs = smf + FLOW_DIM * FLOW_DIM;   // [32][128]
   const long r0 = static_cast<long>(blockIdx.x) * 32;
-  for (int i = threadIdx.x; i < FLOW_DIM * FLOW_DIM / 4; i += 256)
-    reinterpret_cast<float4*>(Ms)[i] = reinterpret_cast<const float4*>(M)[i];
+  if (transpose) {   // backward pass: g_in = g_out M^T
+    for (int i = threadIdx.x; i < FLOW_DIM * FLOW_DIM; i += 256) Ms[(i % FLOW_DIM) * FLOW_DIM + i / FLOW_DIM] = M[i];
+  } else {
+    for (int i = threadIdx.x; i < FLOW_DIM * FLOW_DIM / 4; i += 256)
+      reinterpret_cast<float4*>(Ms)[i] = reinterpret_cast<const float4*>(M)[i];
+  }
   for (int i = threadIdx.x; i < 32 * FLOW_DIM / 4; i += 256) {
     const long row = r0 + (i * 4) / FLOW_DIM;
     reinterpret_cast<float4*>(Xs)[i] =
-        row < rows ? reinterpret_cast<const float4*>(z + r0 * FLOW_DIM)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        row < rows ? reinterpret_cast<const float4*>(z_in + r0 * FLOW_DIM)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
   const int tx = threadIdx.x & 31;   // columns tx*4 .. +3
@@ -298,17 +311,19 @@ flow_linear_kernel(float* __restrict__ z, __half* __restrict__ z_h, const float*
       acc[a][3] = fmaf(x, m.w, acc[a][3]);
     }
   }
-  const float4 cc = *reinterpret_cast<const float4*>(c + tx * 4);
+  const float4 cc = c ? *reinterpret_cast<const float4*>(c + tx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const long row = r0 + ty * 4 + a;
     if (row < rows) {
       const float4 o = make_float4(acc[a][0] + cc.x, acc[a][1] + cc.y, acc[a][2] + cc.z, acc[a][3] + cc.w);
       *reinterpret_cast<float4*>(z + row * FLOW_DIM + tx * 4) = o;
-      uint2 u;
-      u.x = pack_half2(o.x, o.y);
-      u.y = pack_half2(o.z, o.w);
-      *reinterpret_cast<uint2*>(z_h + row * FLOW_DIM + tx * 4) = u;
+      if (z_h) {
+        uint2 u;
+        u.x = pack_half2(o.x, o.y);
+        u.y = pack_half2(o.z, o.w);
+        *reinterpret_cast<uint2*>(z_h + row * FLOW_DIM + tx * 4) = u;
+      }
     }
   }
 }
@@ -404,7 +419,8 @@ __global__ void colstats_partial_kernel(const float* __restrict__ x, long rows, 
 __global__ void bn_train_finalize_kernel(const float* __restrict__ partial, int ntile, long rows, int C,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          float* __restrict__ moving_mean, float* __restrict__ moving_var, float momentum,
-                                         float eps, float* __restrict__ scale, float* __restrict__ shift, int update) {
+                                         float eps, float* __restrict__ scale, float* __restrict__ shift, int update,
+                                         float* __restrict__ save_mean = nullptr, float* __restrict__ save_rstd = nullptr) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
@@ -417,6 +433,10 @@ __global__ void bn_train_finalize_kernel(const float* __restrict__ partial, int 
   const float sc = gamma[c] * rsqrtf(static_cast<float>(var) + eps);
   scale[c] = sc;
   shift[c] = beta[c] - static_cast<float>(mean) * sc;
+  if (save_mean) {
+    save_mean[c] = static_cast<float>(mean);
+    save_rstd[c] = rsqrtf(static_cast<float>(var) + eps);
+  }
   if (update) {
     moving_mean[c] = moving_mean[c] * momentum + static_cast<float>(mean) * (1.f - momentum);
     moving_var[c] = moving_var[c] * momentum + static_cast<float>(var) * (1.f - momentum);

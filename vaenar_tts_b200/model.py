@@ -442,8 +442,8 @@ class VAENAR:
         ll = torch.empty_like(l2)
         ali = torch.empty(nb, B, H, Tz, Tt, dtype=torch.float32, device=self.device) if return_alignments else None
         if training:
-            # forward with training=True semantics (BN batch statistics + moving-average update, dropout).
-            # NOTE: forward only -- the backward pass / optimiser step are not implemented on the CUDA path yet.
+            # forward with training=True semantics (BN batch statistics + moving-average update, dropout);
+            # gradients: train_step_grads / train_step.
             opts, keep = self._train_opts(dropout_masks, update_bn_stats)
             check(self._lib.vaenar_elbo_fwd_train(
                 self._h, self._p(self._flat), self._p(self._packed), self._p(self._ws), self._ws.numel(), self._p(texts),
@@ -461,6 +461,62 @@ class VAENAR:
         return mel, l2, kl, ll, self._ali_dict(ali)
 
     __call__ = call
+
+    # ------------------------------------------------------------------ training (train.py:120-138)
+    DEFAULT_LOSS_SCALE = 65536.0
+
+    def train_step_grads(self, texts, mels, t_lengths, m_lengths, kl_weight, reduction_factor, eps=None,
+                         dropout_masks=None, update_bn_stats=True, loss_scale=None, return_mel=False):
+        """Forward (training=True) + hand-written backward of the train_step closure (train.py:127-136).
+        Returns (losses, grads[, mel]): ``losses`` = device tensor [total, mel_l2, kl, length_l2]; ``grads`` = flat
+        gradient buffer in the layout of ``flat_parameters()``, multiplied by ``loss_scale``."""
+        rf = int(reduction_factor)
+        texts = self._i32(texts)
+        mels = self._f32(mels)
+        B, Tt = texts.shape
+        Tm = mels.shape[1]
+        Tz = (Tm + rf - 1) // rf
+        m_len = self._i32(m_lengths)
+        t_len = self._i32(t_lengths)
+        z_len = (m_len + (rf - 1)) // rf
+        self._prepare(B, Tt, Tz, rf)
+        need = int(self._lib.vaenar_train_workspace_bytes(self._h, B, Tt, Tz, rf))
+        if need < 0:
+            check(-1)
+        if getattr(self, "_train_ws", None) is None or self._train_ws.numel() < need:
+            self._train_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        if getattr(self, "_grads", None) is None:
+            self._grads = torch.zeros_like(self._flat)
+            self._losses = torch.zeros(4, dtype=torch.float32, device=self.device)
+        L, O = self._hp.latent_dim, self._hp.out_dim
+        e = self._noise((B, Tz, L)) if eps is None else self._f32(eps).reshape(B, Tz, L).contiguous()
+        mel = torch.empty(B, Tm, O, dtype=torch.float32, device=self.device) if return_mel else None
+        S = float(self.DEFAULT_LOSS_SCALE if loss_scale is None else loss_scale)
+        opts, keep = self._train_opts(dropout_masks, update_bn_stats)
+        check(self._lib.vaenar_train_step_grads(
+            self._h, self._p(self._flat), self._p(self._packed), self._p(self._train_ws), self._train_ws.numel(),
+            self._p(texts), self._p(mels), self._p(m_len), self._p(t_len), self._p(z_len), self._p(e), B, Tt, Tm, Tz, rf,
+            ctypes.byref(opts), float(kl_weight), float(self.hps.Train.length_weight), S, self._p(self._grads),
+            self._p(self._losses), self._p(mel), self._stream()))
+        if update_bn_stats:
+            self._dirty = True
+        self._last_loss_scale = S
+        return (self._losses, self._grads, mel) if return_mel else (self._losses, self._grads)
+
+    def train_step(self, texts, mels, t_lengths, m_lengths, kl_weight, reduction_factor, eps=None, dropout_masks=None,
+                   loss_scale=None, group=None):
+        """The train_step closure of train.py:120-138: loss, gradients, (data-parallel: ONE all-reduce of the flat
+        gradient buffer over NCCL), Keras Adam.  Returns (loss, mel_l2, kl, length_l2) as a device tensor view."""
+        import torch.distributed as dist
+        losses, grads = self.train_step_grads(texts, mels, t_lengths, m_lengths, kl_weight, reduction_factor, eps=eps,
+                                              dropout_masks=dropout_masks, loss_scale=loss_scale)
+        world = 1
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            world = dist.get_world_size(group)
+            dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=group)      # the single collective of the training path
+        self._opt_step = getattr(self, "_opt_step", 0) + 1
+        self.apply_gradients(grads, self._opt_step, grad_scale=1.0 / (self._last_loss_scale * world))
+        return losses[0], losses[1], losses[2], losses[3]
 
     def init(self, text_inputs, mel_lengths, text_lengths=None, epsilon=None, dropout_masks=None):
         """VAENAR.init (models/models.py:212-226): data-dependent ActNorm initialisation at
