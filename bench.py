@@ -282,6 +282,125 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """Secondary workload (BASELINE.json configs[2], "C3"): LJSpeech hparams, batch 32 per GPU, full train_step
+    (forward + ELBO + hand-written backward + one NCCL all-reduce of the flat gradients when N > 1 + Keras Adam + operand
+    re-pack).  Same JSON contract; `value` = mel frames per second of training."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from vaenar_tts_b200 import VAENAR, LJHPS, _lib
+    lib = _lib.load()
+    from oracle.vaenar_oracle import synthetic_batch
+    from oracle.hparams import LJHPS as OH
+    B, Tt, Tm, rf = args.train_batch, T_TEXT, T_MEL, RF
+    dev = f"cuda:{local}"
+    texts, mels, t_len, m_len = synthetic_batch(OH, B, Tt, Tm, seed=OH.Train.random_seed + rank)
+    h_texts, h_mels = texts.pin_memory(), mels.pin_memory()
+    d_texts, d_mels, d_t, d_m = (x.to(dev) for x in (texts, mels, t_len, m_len))
+    model = VAENAR(LJHPS, device=dev, seed=OH.Train.random_seed)
+    model.init(d_texts, d_m, d_t)                       # init_step of train.py:172-179 (data-dependent ActNorm)
+    klw = float(OH.Train.kl_weight_init) if hasattr(OH.Train, "kl_weight_init") else 1e-5
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_dev():
+        return model.train_step(d_texts, d_mels, d_t, d_m, klw, rf)
+
+    def step_e2e():
+        out = model.train_step(h_texts.to(dev, non_blocking=True), h_mels.to(dev, non_blocking=True), d_t, d_m, klw, rf)
+        return torch.stack(out).cpu()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    n0 = lib.vaenar_launch_count()
+    step_dev()
+    torch.cuda.synchronize()
+    launches = lib.vaenar_launch_count() - n0
+    for _ in range(max(args.warmup, 3) - 1):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        step_dev()
+        b.record()
+    torch.cuda.synchronize()
+    ms_dev = sum(a.elapsed_time(b) for a, b in evs)
+    barrier()
+    ms_e2e = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        losses = step_e2e()
+        ms_e2e += (time.perf_counter() - t0) * 1e3
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    frames_total = world * B * Tm * args.steps
+    if rank == 0:
+        pk = peaks()
+        lib.vaenar_profile_enable(1)
+        step_dev()
+        rep = json.loads(lib.vaenar_profile_report().decode())
+        lib.vaenar_profile_enable(0)
+        tot_ms = sum(v["ms"] for v in rep.values()) or 1.0
+        classes = {k: {"launches_per_step": v["launches"], "ms_per_step": v["ms"], "share": v["ms"] / tot_ms,
+                       "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12, "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9}
+                   for k, v in rep.items() if v["ms"] > 0}
+        dom = max(rep, key=lambda k: rep[k]["ms"])
+        achieved = classes[dom]["tflops"]
+        flops_per_frame = 91.66e6           # SURVEY.md §8d: C3 train step (fwd + bwd = 3 x fwd), rf = 2
+        step_tflops = flops_per_frame * B * Tm / (ms_dev / args.steps * 1e-3) / 1e12
+        line = {
+            "metric": "mel-frames/sec", "value": frames_total / (ms_dev / 1e3), "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate (residual streams, LN/BN/softmax statistics, flow, Adam in f32)",
+            "data": "synthetic",
+            "config": {"workload": f"C3: LJSpeech hparams, batch={B}/GPU, T_text={Tt}, T_mel={Tm}, full train_step "
+                       "(encoder + posterior + prior flow + decoder + KL, backward, Adam), rf=2", "batch_per_gpu": B,
+                       "parallelism": f"dp{world} (one NCCL all-reduce of the flat gradient buffer)" if world > 1 else "single GPU",
+                       "l2": "flushed between timed steps", "execution": "eager C-ABI launch sequence"},
+            "e2e": {"value": frames_total / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(h_texts.numel() * 4 + h_mels.numel() * 4), "d2h_bytes_per_step": 16},
+            "gpu_launches": int(launches * args.steps), "launches_per_step": int(launches), "clocks": clocks,
+            "losses_last_step": [float(x) for x in losses],
+            "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["tflops"], "peak_source": pk["source"] + " cuBLAS bf16 burst", "traffic": None,
+                         "classes": classes,
+                         "whole_step": {"tflops": step_tflops, "frac_of_sustained": step_tflops / pk["tflops_sustained"]}},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -289,9 +408,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs only)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2 (default, the BASELINE.json metric): inference; c3: full train_step")
+    ap.add_argument("--train-batch", type=int, default=32, help="per-GPU batch of the c3 workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c3":
+        run_train(args)
     else:
         run_ours(args)
 

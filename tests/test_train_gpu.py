@@ -160,3 +160,25 @@ def test_gradients_c1_size():
     assert abs(float(losses[0]) - float(loss.detach())) <= 2e-3 * abs(float(loss.detach()))
     bad, worst = compare(got, ref, ref16)
     assert not bad, (len(bad), bad[:12], worst)
+
+
+def test_training_loop_reduces_loss():
+    """init_step + 40 train_steps (train.py:246-266, 182-204) on one small batch with on-device dropout / noise: the
+    loss goes down and everything stays finite (the optimiser, the re-packing of the operands and the BatchNorm moving
+    averages are all exercised)."""
+    case = list(CASES)[0]
+    ohps, g, P = load_case(case)
+    m = make_model(ohps, O.init_params(ohps, seed=3))          # Keras-default init incl. the zero-init projections
+    args = (t(g, "texts"), t(g, "mels"), t(g, "t_len"), t(g, "m_len"))
+    m.init(args[0], args[3], args[2])
+    first = last = None
+    for step in range(40):
+        loss, l2, kl, ll = m.train_step(*args, 1e-5, int(g["rf"]))
+        v = [float(x) for x in (loss, l2, kl, ll)]
+        assert all(x == x and abs(x) < 1e6 for x in v), (step, v)
+        if step == 0:
+            first = v
+        last = v
+    assert last[0] < 0.8 * first[0], (first, last)
+    mel, _ = m.inference(args[0], args[3], args[2], reduction_factor=int(g["rf"]))
+    assert torch.isfinite(mel).all()
