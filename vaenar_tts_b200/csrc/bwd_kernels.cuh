@@ -101,69 +101,168 @@ ln_bwd_kernel(const float* dy, const float* __restrict__ y, const float* __restr
   }
 }
 
-// ------------------------------------------------------------------ activation / dropout backward + bias gradient
-__device__ __forceinline__ float ld_as_float(const float* p, long i) { return p[i]; }
-__device__ __forceinline__ float ld_as_float(const __half* p, long i) { return __half2float(p[i]); }
+// ------------------------------------------------------------------ column-wise kernels: thread layout
+// 256 threads over a row-major [rows, C] tile = `lanes` row lanes x `groups` column groups of V consecutive columns
+// (vector loads, coalesced along the row); per-column sums are combined across the lanes through shared memory in a
+// fixed order.  C must be a multiple of V and C / V <= 256.
+template <int V>
+struct ColLayout {
+  int groups, lanes, g, lane;
+  bool active;
+  __device__ explicit ColLayout(int C) {
+    groups = C / V;
+    lanes = 256 / groups;
+    g = threadIdx.x % groups;
+    lane = threadIdx.x / groups;
+    active = lane < lanes;
+  }
+};
+__device__ __forceinline__ void ld8(const float* p, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const __half* p, float* v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __half22float2(h[e]);
+    v[2 * e] = f.x; v[2 * e + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void st8h(__half* p, const float* v) {
+  uint4 u;
+  u.x = pack_half2(v[0], v[1]); u.y = pack_half2(v[2], v[3]); u.z = pack_half2(v[4], v[5]); u.w = pack_half2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
 
+// ------------------------------------------------------------------ activation / dropout backward + bias gradient
 // out_h = g * mask * [act > 0]   (mask nullable: inverted-dropout keep mask; act: post-ReLU (and post-dropout) activation),
-// dbias[c] += column sums (split destinations: columns >= split go to dbias1[c - split]).  128 rows per CTA.
-// out_h may alias g when TG == __half.
+// dbias[c] += column sums.  64 rows per CTA, 8 columns per thread; C % 8 == 0, C <= 2048.  out_h may alias g (TG == __half).
 template <typename TG>
 __global__ void __launch_bounds__(256)
 relu_bwd_kernel(const TG* g, const float* __restrict__ mask, const __half* __restrict__ act, long rows, int C,
                 __half* out_h, float* __restrict__ dbias) {
-  const long r0 = static_cast<long>(blockIdx.x) * 128;
-  const long r1 = min(rows, r0 + 128);
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float s = 0.f;
-    for (long r = r0; r < r1; ++r) {
-      const long i = r * C + c;
-      float v = ld_as_float(g, i);
-      if (mask) v *= mask[i];
-      if (act && !(__half2float(act[i]) > 0.f)) v = 0.f;
-      out_h[i] = __float2half_rn(v);
-      s += v;
+  __shared__ float red[256 * 8];
+  const ColLayout<8> L(C);
+  const long r0 = static_cast<long>(blockIdx.x) * 64;
+  const long r1 = min(rows, r0 + 64);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (L.active)
+    for (long r = r0 + L.lane; r < r1; r += L.lanes) {
+      const long i = r * C + L.g * 8;
+      float v[8], a[8];
+      ld8(g + i, v);
+      if (mask) {
+        float m[8];
+        ld8(mask + i, m);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= m[e];
+      }
+      if (act) {
+        ld8(act + i, a);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = a[e] > 0.f ? v[e] : 0.f;
+      }
+      st8h(out_h + i, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v[e];
     }
-    if (dbias) atomicAdd(dbias + c, s);
+  if (dbias) {
+    __syncthreads();
+    if (L.active)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[L.lane * C + L.g * 8 + e] = acc[e];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float t = 0.f;
+      for (int l = 0; l < L.lanes; ++l) t += red[l * C + c];
+      atomicAdd(dbias + c, t);
+    }
   }
 }
 
 // Column sums of a row-major [rows, ld] tensor window of C columns: out0[c] += sum (c < split), out1[c - split] otherwise.
-template <typename T>
+// 128 rows per CTA; V = 4 (float) / 8 (half) columns per thread.
+template <typename T, int V>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ in, long rows, int C, int ld, float* __restrict__ out0, int split,
               float* __restrict__ out1) {
+  __shared__ float red[256 * V];
+  const ColLayout<V> L(C);
   const long r0 = static_cast<long>(blockIdx.x) * 128;
   const long r1 = min(rows, r0 + 128);
+  float acc[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) acc[e] = 0.f;
+  if (L.active)
+    for (long r = r0 + L.lane; r < r1; r += L.lanes) {
+      float v[8];
+      if constexpr (V == 8) {
+        ld8(in + r * ld + L.g * 8, v);
+      } else {
+        const float4 a = *reinterpret_cast<const float4*>(in + r * ld + L.g * 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] += v[e];
+    }
+  __syncthreads();
+  if (L.active)
+#pragma unroll
+    for (int e = 0; e < V; ++e) red[L.lane * C + L.g * V + e] = acc[e];
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += 256) {
-    float s = 0.f;
-    for (long r = r0; r < r1; ++r) s += ld_as_float(in, r * ld + c);
-    if (c < split) atomicAdd(out0 + c, s);
-    else atomicAdd(out1 + (c - split), s);
+    float t = 0.f;
+    for (int l = 0; l < L.lanes; ++l) t += red[l * C + c];
+    if (c < split) atomicAdd(out0 + c, t);
+    else atomicAdd(out1 + (c - split), t);
   }
 }
 
 // ------------------------------------------------------------------ BatchNorm (training mode) backward
 // Forward (modules/utils.py:56-85): a = act(conv + bias);  xhat = (a - mean) * rstd;  out = (gamma*xhat + beta) * mask.
 // partial[tile][0][c] = sum dy', partial[tile][1][c] = sum dy' * xhat with dy' = dout * mask  (fixed-order, deterministic)
-__global__ void bn_bwd_stats_kernel(const float* __restrict__ dout, const float* __restrict__ mask,
-                                    const float* __restrict__ a, const float* __restrict__ mean,
-                                    const float* __restrict__ rstd, long rows, int C, int rows_per_tile,
-                                    float* __restrict__ partial) {
+// 4 columns per thread; C % 4 == 0, C <= 1024.
+__global__ void __launch_bounds__(256)
+bn_bwd_stats_kernel(const float* __restrict__ dout, const float* __restrict__ mask, const float* __restrict__ a,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, long rows, int C, int rows_per_tile,
+                    float* __restrict__ partial) {
+  __shared__ float red[256 * 4];
+  const ColLayout<4> L(C);
   const long r0 = static_cast<long>(blockIdx.x) * rows_per_tile;
   const long r1 = min(rows, r0 + rows_per_tile);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float mu = mean[c], rs = rstd[c];
-    float s = 0.f, q = 0.f;
-    for (long r = r0; r < r1; ++r) {
-      const long i = r * C + c;
-      float d = dout[i];
-      if (mask) d *= mask[i];
-      s += d;
-      q = fmaf(d, (a[i] - mu) * rs, q);
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  if (L.active) {
+    const float4 mu = *reinterpret_cast<const float4*>(mean + L.g * 4), rs = *reinterpret_cast<const float4*>(rstd + L.g * 4);
+    const float mu4[4] = {mu.x, mu.y, mu.z, mu.w}, rs4[4] = {rs.x, rs.y, rs.z, rs.w};
+    for (long r = r0 + L.lane; r < r1; r += L.lanes) {
+      const long i = r * C + L.g * 4;
+      float4 d = *reinterpret_cast<const float4*>(dout + i);
+      if (mask) {
+        const float4 m = *reinterpret_cast<const float4*>(mask + i);
+        d.x *= m.x; d.y *= m.y; d.z *= m.z; d.w *= m.w;
+      }
+      const float4 av = *reinterpret_cast<const float4*>(a + i);
+      const float d4[4] = {d.x, d.y, d.z, d.w}, a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        s[e] += d4[e];
+        q[e] = fmaf(d4[e], (a4[e] - mu4[e]) * rs4[e], q[e]);
+      }
     }
-    partial[(static_cast<long>(blockIdx.x) * 2 + 0) * C + c] = s;
-    partial[(static_cast<long>(blockIdx.x) * 2 + 1) * C + c] = q;
+  }
+  for (int which = 0; which < 2; ++which) {
+    __syncthreads();
+    if (L.active)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) red[L.lane * C + L.g * 4 + e] = which ? q[e] : s[e];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float t = 0.f;
+      for (int l = 0; l < L.lanes; ++l) t += red[l * C + c];
+      partial[(static_cast<long>(blockIdx.x) * 2 + which) * C + c] = t;
+    }
   }
 }
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int ntile, int C, float* __restrict__ s1,
@@ -181,30 +280,57 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nt
   dgamma[c] += static_cast<float>(q);
 }
 // da = gamma*rstd*(dy' - s1/N - xhat*s2/N);  dpre = da * act'(a)  (act 1: relu, 2: tanh, 0: identity) -> fp16 operand of
-// the conv dgrad / wgrad, plus the conv bias gradient (column sums).  128 rows per CTA.
+// the conv dgrad / wgrad, plus the conv bias gradient (column sums).  64 rows per CTA, 4 columns per thread.
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ mask, const float* __restrict__ a,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                     const float* __restrict__ s1, const float* __restrict__ s2, long rows, int C, int act,
                     __half* __restrict__ dpre_h, float* __restrict__ dbias) {
-  const long r0 = static_cast<long>(blockIdx.x) * 128;
-  const long r1 = min(rows, r0 + 128);
+  __shared__ float red[256 * 4];
+  const ColLayout<4> L(C);
+  const long r0 = static_cast<long>(blockIdx.x) * 64;
+  const long r1 = min(rows, r0 + 64);
   const float inv_n = 1.0f / static_cast<float>(rows);
-  for (int c = threadIdx.x; c < C; c += 256) {
-    const float mu = mean[c], rs = rstd[c], gr = gamma[c] * rs, m1 = s1[c] * inv_n, m2 = s2[c] * inv_n;
-    float s = 0.f;
-    for (long r = r0; r < r1; ++r) {
-      const long i = r * C + c;
-      float d = dout[i];
-      if (mask) d *= mask[i];
-      const float av = a[i];
-      float v = gr * (d - m1 - (av - mu) * rs * m2);
-      if (act == 1) v = av > 0.f ? v : 0.f;
-      else if (act == 2) v *= 1.f - av * av;
-      dpre_h[i] = __float2half_rn(v);
-      s += v;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (L.active) {
+    float mu[4], rs[4], gr[4], m1[4], m2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = L.g * 4 + e;
+      mu[e] = mean[c]; rs[e] = rstd[c]; gr[e] = gamma[c] * rs[e]; m1[e] = s1[c] * inv_n; m2[e] = s2[c] * inv_n;
     }
-    atomicAdd(dbias + c, s);
+    for (long r = r0 + L.lane; r < r1; r += L.lanes) {
+      const long i = r * C + L.g * 4;
+      float4 d = *reinterpret_cast<const float4*>(dout + i);
+      if (mask) {
+        const float4 m = *reinterpret_cast<const float4*>(mask + i);
+        d.x *= m.x; d.y *= m.y; d.z *= m.z; d.w *= m.w;
+      }
+      const float4 av = *reinterpret_cast<const float4*>(a + i);
+      const float d4[4] = {d.x, d.y, d.z, d.w}, a4[4] = {av.x, av.y, av.z, av.w};
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[e] = gr[e] * (d4[e] - m1[e] - (a4[e] - mu[e]) * rs[e] * m2[e]);
+        if (act == 1) v[e] = a4[e] > 0.f ? v[e] : 0.f;
+        else if (act == 2) v[e] *= 1.f - a4[e] * a4[e];
+        acc[e] += v[e];
+      }
+      uint2 u;
+      u.x = pack_half2(v[0], v[1]);
+      u.y = pack_half2(v[2], v[3]);
+      *reinterpret_cast<uint2*>(dpre_h + i) = u;
+    }
+  }
+  __syncthreads();
+  if (L.active)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) red[L.lane * C + L.g * 4 + e] = acc[e];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float t = 0.f;
+    for (int l = 0; l < L.lanes; ++l) t += red[l * C + c];
+    atomicAdd(dbias + c, t);
   }
 }
 
@@ -428,38 +554,52 @@ flow_param_grad_kernel(const float* __restrict__ G_all, const float* __restrict_
 }
 
 // ------------------------------------------------------------------ positional weight / embedding / misc
-// dpw += sum_{rows, c} g[row, c] * table[t(row), c]   (x = dense(...) + pos_weight * PE, encoder.py:84-86 etc.)
+// dpw += sum_{rows, c} g[row, c] * table[t(row), c]   (x = dense(...) + pos_weight * PE, encoder.py:84-86 etc.); C % 4 == 0
 __global__ void __launch_bounds__(256)
 pe_dot_kernel(const float* __restrict__ g, const float* __restrict__ mask, const float* __restrict__ table, long rows, int T,
               int C, float* __restrict__ dpw) {
   __shared__ float sh[32];
-  const long n = rows * C;
+  const long n4 = rows * C / 4;
+  const int c4 = C / 4;
   float acc = 0.f;
-  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long row = i / C;
-    const int c = static_cast<int>(i % C), t = static_cast<int>(row % T);
-    float v = g[i];
-    if (mask) v *= mask[i];
-    acc = fmaf(v, table[static_cast<long>(t) * C + c], acc);
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long row = i / c4;
+    const int c = static_cast<int>(i - row * c4) * 4, t = static_cast<int>(row % T);
+    float4 v = *reinterpret_cast<const float4*>(g + i * 4);
+    if (mask) {
+      const float4 m = *reinterpret_cast<const float4*>(mask + i * 4);
+      v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+    }
+    const float4 p = *reinterpret_cast<const float4*>(table + static_cast<long>(t) * C + c);
+    acc += v.x * p.x + v.y * p.y + v.z * p.z + v.w * p.w;
   }
   const float tot = block_sum(acc, sh);
   if (threadIdx.x == 0) atomicAdd(dpw, tot);
 }
 
 // Embedding gradient (modules/encoder.py:10-12,81): dE[v, :] += sum over tokens with id v of g[token, :].
-// grid (V, ceil(C / 128)), deterministic.
-__global__ void embed_bwd_kernel(const int* __restrict__ ids, const float* __restrict__ g, long rows, int C, int V,
-                                 float* __restrict__ dE) {
+// grid (V, C / 32); 256 threads = 32 columns x 8 row lanes, lanes combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+embed_bwd_kernel(const int* __restrict__ ids, const float* __restrict__ g, long rows, int C, int V, float* __restrict__ dE) {
+  __shared__ float red[8][32];
   const int v = blockIdx.x;
-  const int c = blockIdx.y * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + cl;
   float s = 0.f;
-  for (long r = 0; r < rows; ++r) {
-    int id = ids[r];
-    id = min(max(id, 0), V - 1);
-    if (id == v) s += g[r * C + c];
+  if (c < C)
+    for (long r = lane; r < rows; r += 8) {
+      int id = ids[r];
+      id = min(max(id, 0), V - 1);
+      if (id == v) s += g[r * C + c];
+    }
+  red[lane][cl] = s;
+  __syncthreads();
+  if (lane == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) t += red[l][cl];
+    dE[static_cast<long>(v) * C + c] += t;
   }
-  dE[static_cast<long>(v) * C + c] += s;
 }
 
 // out = a + b (fp32) ; optional fp16 copy

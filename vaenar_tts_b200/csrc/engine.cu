@@ -1091,7 +1091,7 @@ static void conv_bn(Ctx& c, const std::string& pk, const std::string& pn, AOp a0
   float* y = c.alloc<float>(rows * C);
   p.out_f32 = y; p.ld_f32 = C;
   run_gemm(c, block_n, a0, a1, B, T, c.W(pk), c.WM(pk).K, C, p);
-  const int rpt = 256, ntile = static_cast<int>(cdiv(static_cast<int>(rows), rpt));
+  const int rpt = 64, ntile = static_cast<int>(cdiv(static_cast<int>(rows), rpt));
   float* partial = c.alloc<float>(static_cast<int64_t>(ntile) * 2 * C);
   float* scale = c.alloc<float>(C);
   float* shift = c.alloc<float>(C);
@@ -1304,14 +1304,14 @@ static void prior_init(Ctx& c, const float* text_embd, const int* t_len, const i
   const int64_t rows = static_cast<int64_t>(B) * Tz;
   const int64_t mark = c.ws_off;
   PriorBufs b = prior_setup(c, text_embd, B, Tt, Tz);
-  const int rpt = 256, ntile = cdiv(static_cast<int>(rows), rpt);
+  const int rpt = 64, ntile = cdiv(static_cast<int>(rows), rpt);
   float* partial = c.alloc<float>(static_cast<int64_t>(ntile) * 2 * L);
   float* Mf = c.dry ? nullptr : reinterpret_cast<float*>(c.packed + c.m->off_Mf);
   float* cf = c.dry ? nullptr : reinterpret_cast<float*>(c.packed + c.m->off_cf);
   for (int s = 0; s < h.prior_n_blk; ++s) {
     const std::string g = "prior.glow." + std::to_string(s);
     if (!c.dry) {
-      colstats_partial_kernel<<<ntile, 128, 0, c.stream>>>(z, rows, L, rpt, partial);
+      colstats_partial_kernel<<<ntile, 256, 0, c.stream>>>(z, rows, L, rpt, partial);
       actnorm_init_kernel<<<1, FLOW_DIM, 0, c.stream>>>(partial, ntile, rows, c.PM(g + ".actnorm.log_scale"),
                                                        c.PM(g + ".actnorm.bias"), c.P(g + ".linear.weight"),
                                                        Mf + static_cast<int64_t>(s) * L * L, cf + s * L);
@@ -1533,8 +1533,9 @@ static void elbo_fwd(Ctx& c, const int* texts, const float* mels, const int* m_l
   prior_logprob(c, z, emb, t_len, z_len, B, Tt, Tz, logp);
   if (!c.dry) {
     length_loss_kernel<<<cdiv(B, 128), 128, 0, c.stream>>>(pred, m_len, len_loss, B);
-    l2_loss_kernel<<<B, 256, 0, c.stream>>>(fin, Tz * rf, mels, Tm, m_len, l2, O, 0);
-    l2_loss_kernel<<<B, 256, 0, c.stream>>>(ini, Tz * rf, mels, Tm, m_len, l2, O, 1);
+    VB_CUDA(cudaMemsetAsync(l2, 0, B * sizeof(float), c.stream));
+    l2_loss_kernel<<<dim3(B, 16), 256, 0, c.stream>>>(fin, Tz * rf, mels, Tm, m_len, l2, O);
+    l2_loss_kernel<<<dim3(B, 16), 256, 0, c.stream>>>(ini, Tz * rf, mels, Tm, m_len, l2, O);
     kl_kernel<<<cdiv(B, 128), 128, 0, c.stream>>>(logq, logp, kl, B);
     check_launch("loss kernels");
     VB_CUDA(cudaMemcpy2DAsync(mel_out, static_cast<size_t>(Tm) * O * 4, fin, static_cast<size_t>(Tz) * rf * O * 4,

@@ -377,41 +377,54 @@ __global__ void row_sum_kernel(const float* __restrict__ row_acc, float* __restr
 
 // VAENAR._compute_l2_loss per batch element (models/models.py:67-86, n_sample = 1):
 //   out[b] (+)= sum_{t < len} mean_d (rec - tgt)^2 / len
+// grid (B, chunks): every CTA reduces a slice of the frames and adds its share (out must be zeroed by the caller).
 __global__ void l2_loss_kernel(const float* __restrict__ rec, int rec_T, const float* __restrict__ tgt, int tgt_T,
-                               const int* __restrict__ lens, float* __restrict__ out, int D, int accumulate) {
+                               const int* __restrict__ lens, float* __restrict__ out, int D) {
   __shared__ float sh[32];
   const int b = blockIdx.x;
   const int len = min(lens[b], tgt_T);
+  const long n = static_cast<long>(len) * D;
   float acc = 0.f;
-  for (long i = threadIdx.x; i < static_cast<long>(len) * D; i += blockDim.x) {
+  for (long i = static_cast<long>(blockIdx.y) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.y) * blockDim.x) {
     const int t = static_cast<int>(i / D), d = static_cast<int>(i % D);
     const float df = rec[(static_cast<long>(b) * rec_T + t) * D + d] - tgt[(static_cast<long>(b) * tgt_T + t) * D + d];
     acc += df * df;
   }
   const float tot = block_sum(acc, sh);
-  if (threadIdx.x == 0) {
-    const float v = tot / static_cast<float>(D) / static_cast<float>(lens[b]);
-    out[b] = accumulate ? out[b] + v : v;
-  }
+  if (threadIdx.x == 0) atomicAdd(out + b, tot / static_cast<float>(D) / static_cast<float>(lens[b]));
 }
 
 // ------------------------------------------------------------------ training-mode BatchNorm / dropout / ActNorm init
 // Per-channel partial sums over a tile of rows: partial[tile][0][c] = sum x, partial[tile][1][c] = sum x^2.
 // (Keras BatchNormalization in training mode normalises with the batch mean / population variance over
 // (batch, time) INCLUDING padded frames, modules/utils.py:72,79-83.)
-__global__ void colstats_partial_kernel(const float* __restrict__ x, long rows, int C, int rows_per_tile,
-                                        float* __restrict__ partial) {
+// 256 threads = row lanes x column groups of 4 (float4 loads); lanes combined in a fixed order.  C % 4 == 0, C <= 1024.
+__global__ void __launch_bounds__(256)
+colstats_partial_kernel(const float* __restrict__ x, long rows, int C, int rows_per_tile, float* __restrict__ partial) {
+  __shared__ float red[256 * 4];
+  const int groups = C / 4, lanes = 256 / groups;
+  const int g = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const bool active = lane < lanes;
   const long r0 = static_cast<long>(blockIdx.x) * rows_per_tile;
   const long r1 = min(rows, r0 + rows_per_tile);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f, q = 0.f;
-    for (long r = r0; r < r1; ++r) {
-      const float v = x[r * C + c];
-      s += v;
-      q = fmaf(v, v, q);
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active)
+    for (long r = r0 + lane; r < r1; r += lanes) {
+      const float4 v = *reinterpret_cast<const float4*>(x + r * C + g * 4);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
     }
-    partial[(static_cast<long>(blockIdx.x) * 2 + 0) * C + c] = s;
-    partial[(static_cast<long>(blockIdx.x) * 2 + 1) * C + c] = q;
+  for (int which = 0; which < 2; ++which) {
+    __syncthreads();
+    if (active)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) red[lane * C + g * 4 + e] = which ? q[e] : s[e];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float t = 0.f;
+      for (int l = 0; l < lanes; ++l) t += red[l * C + c];
+      partial[(static_cast<long>(blockIdx.x) * 2 + which) * C + c] = t;
+    }
   }
 }
 // mean / population variance (float64 accumulation over the tile partials, fixed order => deterministic),
