@@ -123,6 +123,9 @@ struct vaenar_model {
   std::vector<PackOp> host_ops;
   std::vector<const float*> host_ptrs;
   std::vector<float*> host_gptrs;   // flow parameter-gradient pointers (train step)
+  cudaStream_t wgrad_stream = nullptr;   // weight gradients run beside the activation-gradient chain (train step)
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_cursor = 0;
   bool attrs_set = false;
   cudaStream_t side_stream = nullptr;   // second launch chain for batch-split inference (fork/join with events)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -521,6 +524,7 @@ struct Ctx {
   int n_masks = 0, mask_cursor = 0;
   uint64_t seed = 0;
   int update_bn = 1;
+  cudaStream_t wstream = nullptr;        // when set, run_wgrad launches here after an event recorded on `stream`
 
   template <typename T>
   T* alloc(int64_t count) {
@@ -759,8 +763,23 @@ struct WOp {
   int C = 0;      // channel extent of the tensor map (columns >= C read as zero)
   int col0 = 0;   // first channel of the operand window
 };
+static cudaEvent_t next_event(vaenar_model* m) {
+  if (m->ev_cursor == m->ev_pool.size()) {
+    cudaEvent_t e;
+    VB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    m->ev_pool.push_back(e);
+  }
+  return m->ev_pool[m->ev_cursor++];
+}
+// everything queued on the weight-gradient stream so far is ordered before what follows on the main stream
+static void join_wgrad(Ctx& c) {
+  if (c.dry || !c.wstream) return;
+  cudaEvent_t e = next_event(c.m);
+  VB_CUDA(cudaEventRecord(e, c.wstream));
+  VB_CUDA(cudaStreamWaitEvent(c.stream, e, 0));
+}
 static void run_wgrad(Ctx& c, WOp x0, WOp x1, int a_split, WOp dy, int batches, int rows, int shift, int M, int N,
-                      float* out, int ldo) {
+                      float* out, int ldo, const std::vector<float*>* outs = nullptr, int n_per_out = 0) {
   if (c.dry) return;
   WgradParams p;
   memset(&p, 0, sizeof(p));
@@ -768,7 +787,7 @@ static void run_wgrad(Ctx& c, WOp x0, WOp x1, int a_split, WOp dy, int batches, 
   p.kb_per_batch = cdiv(rows, WG_BLOCK_K);
   p.total_kb = batches * p.kb_per_batch;
   const int tiles = cdiv(M, WG_BLOCK_M) * cdiv(N, WG_BLOCK_N);
-  int splits = std::max(1, std::min(p.total_kb, cdiv(2 * 148, tiles)));   // about two waves of CTAs
+  int splits = std::max(1, std::min(p.total_kb, std::max(1, 148 / tiles)));   // about one wave of CTAs
   p.kb_per_split = cdiv(p.total_kb, splits);
   splits = cdiv(p.total_kb, p.kb_per_split);
   p.M = M; p.N = N;
@@ -776,21 +795,33 @@ static void run_wgrad(Ctx& c, WOp x0, WOp x1, int a_split, WOp dy, int batches, 
   p.a_split = a_split; p.a_shift = shift;
   p.a0_col0 = x0.col0; p.a1_col0 = x1.col0; p.b_col0 = dy.col0;
   p.out = out; p.ldo = ldo;
+  if (outs) {
+    if (outs->size() > 24 || n_per_out <= 0) VB_THROW("wgrad: too many output tensors");
+    p.n_per_out = n_per_out;
+    for (size_t i = 0; i < outs->size(); ++i) p.outs[i] = (*outs)[i];
+  }
   if (a_split % WG_BLOCK_M != 0 && a_split != M) VB_THROW("wgrad: concat boundary %d must be a multiple of %d", a_split, WG_BLOCK_M);
   const CUtensorMap tA0 = make_tmap(x0.p, 3, x0.C, rows, batches, x0.ld, static_cast<uint64_t>(rows) * x0.ld, 64, 64);
   const CUtensorMap tA1 = make_tmap(x1.p, 3, x1.C, rows, batches, x1.ld, static_cast<uint64_t>(rows) * x1.ld, 64, 64);
   const CUtensorMap tB = make_tmap(dy.p, 3, dy.C, rows, batches, dy.ld, static_cast<uint64_t>(rows) * dy.ld, 64, 64);
   const double tokens = static_cast<double>(batches) * rows;
-  ProfileScope prof("wgrad", 2.0 * tokens * M * N, tokens * (M + N) * 2 + static_cast<double>(M) * N * 4, c.stream);
+  ProfileScope prof("wgrad", 2.0 * tokens * M * N, tokens * (M + N) * 2 + static_cast<double>(M) * N * 4,
+                    c.wstream ? c.wstream : c.stream);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(cdiv(M, WG_BLOCK_M), cdiv(N, WG_BLOCK_N), splits);
   cfg.blockDim = dim3(WG_THREADS);
   cfg.dynamicSmemBytes = WG_SMEM;
   cfg.stream = c.stream;
+  if (c.wstream) {   // off the critical path: wait for the producer of dY, then run on the weight-gradient stream
+    cudaEvent_t e = next_event(c.m);
+    VB_CUDA(cudaEventRecord(e, c.stream));
+    VB_CUDA(cudaStreamWaitEvent(c.wstream, e, 0));
+    cfg.stream = c.wstream;
+  }
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (g_use_pdl && !c.wstream) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const cudaError_t le = cudaLaunchKernelEx(&cfg, wgrad_tc_kernel, tA0, tA1, tB, p);
@@ -1734,6 +1765,8 @@ int vaenar_create(const vaenar_hparams_t* hps, vaenar_handle_t* out) {
 }
 int vaenar_destroy(vaenar_handle_t h) {
   if (h) {
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->wgrad_stream) cudaStreamDestroy(h->wgrad_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -1909,6 +1942,11 @@ int vaenar_train_step_grads(vaenar_handle_t h, float* params, const void* packed
   if (!(loss_scale > 0.f)) VB_THROW("loss_scale must be positive");
   Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
   apply_train_opts(c, params, opts);
+  if (!getenv("VAENAR_NO_WGRAD_STREAM")) {
+    if (!h->wgrad_stream) VB_CUDA(cudaStreamCreateWithFlags(&h->wgrad_stream, cudaStreamNonBlocking));
+    c.wstream = h->wgrad_stream;
+  }
+  h->ev_cursor = 0;
   train_grads(c, grads, texts, mels, mel_lengths, text_lengths, z_lengths, eps, B, T_text, T_mel, T_z, rf, kl_weight, length_weight,
               loss_scale, losses, mel_out);
   API_END

@@ -40,6 +40,10 @@ struct WgradParams {
   int a0_col0, a1_col0, b_col0;   // first channel of the operand windows inside their tensors
   float* out;              // [M, ldo] fp32, accumulated
   int ldo;
+  // several parameter tensors behind one launch (Q|K|V kernels, the K / V memory projections of all blocks of a module):
+  // column n belongs to outs[n / n_per_out] at local column n % n_per_out (n_per_out == 0: single output `out`)
+  int n_per_out;
+  float* outs[24];
 };
 
 // smem descriptor of an MN-major SW128 tile: start, LBO (64-channel chunk pitch), SBO (8-token group pitch)
@@ -159,9 +163,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         __syncwarp();
         const int col = n0 + c0 + lane;
         if (col < p.N) {
+          float* dst = p.n_per_out ? p.outs[col / p.n_per_out] + (col % p.n_per_out) : p.out + col;
           for (int rr = 0; rr < 32; ++rr) {
             const int row = m0 + quad * 32 + rr;
-            if (row < p.M) atomicAdd(p.out + static_cast<long>(row) * p.ldo + col, tile[rr * 33 + lane]);
+            if (row < p.M) atomicAdd(dst + static_cast<long>(row) * p.ldo, tile[rr * 33 + lane]);
           }
         }
       }
