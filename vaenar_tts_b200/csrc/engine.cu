@@ -252,8 +252,18 @@ static void plan_bw_xblk(vaenar_model& m, const std::string& pk, const std::stri
   for (const char* q : {"query", "key", "value"})
     m.add_op("bw." + pk + ".qkv", 0, (i++) * d, n + ".self_attention." + q + "_layer.kernel", 0, d, d, d, 2);
   plan_bw(m, "bw." + pk + ".proj1", n + ".att_proj1.kernel", 2 * d, d);
-  plan_bw(m, "bw." + pk + ".cq", n + ".cross_attention.query_layer.kernel", d, d);
   plan_bw(m, "bw." + pk + ".proj2", n + ".att_proj2.kernel", 2 * d, d);
+  // K-concatenated operands: all gradient contributions to one residual-stream tensor in ONE GEMM
+  //   d s = du2 Wp2[:d]^T + dq2 Wcq^T                  -> [d, d | d]
+  //   d x = du1 Wp1[:d]^T + dqkv [Wq | Wk | Wv]^T      -> [d, d | 3d]
+  m.add_mat("bw." + pk + ".sq", d, 2 * d);
+  m.add_op("bw." + pk + ".sq", 0, 0, n + ".att_proj2.kernel", 0, d, d, d, 2);
+  m.add_op("bw." + pk + ".sq", 0, d, n + ".cross_attention.query_layer.kernel", 0, d, d, d, 2);
+  m.add_mat("bw." + pk + ".xq", d, 4 * d);
+  m.add_op("bw." + pk + ".xq", 0, 0, n + ".att_proj1.kernel", 0, d, d, d, 2);
+  i = 0;
+  for (const char* q : {"query", "key", "value"})
+    m.add_op("bw." + pk + ".xq", 0, d + (i++) * d, n + ".self_attention." + q + "_layer.kernel", 0, d, d, d, 2);
   plan_bw(m, "bw." + pk + ".ffn1", n + ".ffn.dense1.kernel", d, ffn);
   plan_bw(m, "bw." + pk + ".ffn2", n + ".ffn.dense2.kernel", ffn, d);
 }
@@ -443,6 +453,11 @@ static void build_model(vaenar_model& m) {
       for (const char* q : {"query", "key", "value"})
         m.add_op(pk + ".qkv", 0, (c++) * A, n + ".attention." + q + "_layer.kernel", 0, E, A, A, 2);
       plan_bw(m, pk + ".proj", n + ".att_proj.kernel", E + A, E);
+      m.add_mat(pk + ".xq", E, E + 3 * A);
+      m.add_op(pk + ".xq", 0, 0, n + ".att_proj.kernel", 0, E, E, E, 2);
+      c = 0;
+      for (const char* q : {"query", "key", "value"})
+        m.add_op(pk + ".xq", 0, E + (c++) * A, n + ".attention." + q + "_layer.kernel", 0, E, A, A, 2);
       plan_bw(m, pk + ".ffn1", n + ".ffn.dense1.kernel", E, h.enc_ffn);
       plan_bw(m, pk + ".ffn2", n + ".ffn.dense2.kernel", h.enc_ffn, E);
     }
@@ -609,6 +624,7 @@ struct ProfileScope {
   X(128, EPI_PLAIN, F_BIAS | F_RELU | F_TABLE | F_OUT_F32 | F_OUT_H)                                  \
   X(128, EPI_PLAIN, F_BIAS | F_OUT_F32 | F_OUT_H | F_OUT_LO)                                          \
   X(128, EPI_PLAIN, F_BIAS | F_RES | F_OUT_F32)                                                       \
+  X(128, EPI_PLAIN, F_RES | F_OUT_F32) X(128, EPI_PLAIN, F_OUT_F32)                                   \
   X(128, EPI_LN, 0) X(256, EPI_LN, 0)                                                                \
   X(256, EPI_QKV, F_OUT_H) X(128, EPI_COUPLING, 0) X(256, EPI_POSTERIOR, 0)
 
