@@ -27,4 +27,23 @@ if which in ("all", "gemm"):
     res = torch.randn(M, 256, generator=g); gm = torch.ones(256); bt = torch.zeros(256)
     for _ in range(2):
         G.dense(A2, W2, b2, residual=res, gamma=gm, beta=bt, ln=True, block_n=256)   # FFN dense2 + residual + LN
+if which in ("all", "wgrad"):
+    Bw, T = 32, 435                                                                   # C3 token count
+    X = torch.randn(Bw, T, 256, generator=g); dY = torch.randn(Bw, T, 1024, generator=g)
+    for _ in range(2):
+        G.wgrad(X, dY)                                                                # FFN dense1 weight gradient [256, 1024]
+    dY2 = torch.randn(Bw, T, 256, generator=g)
+    for _ in range(2):
+        G.wgrad(X, dY2, X2=X)                                                         # att_proj ([x ; ctx]) weight gradient [512, 256]
+if which in ("all", "attn_bwd"):
+    Bw = 32
+    q = torch.randn(Bw, Tz, 256, generator=g); k = torch.randn(Bw, Tz, 256, generator=g); v = torch.randn(Bw, Tz, 256, generator=g)
+    do = torch.randn(Bw, Tz, 256, generator=g)
+    ql = torch.randint(300, Tz + 1, (Bw,), generator=g); ql[0] = Tz
+    for _ in range(2):
+        G.attention_bwd(q, k, v, do, ql, ql, H, True)                                 # causal self-attention backward
+    km = torch.randn(Bw, Tt, 256, generator=g); vm = torch.randn(Bw, Tt, 256, generator=g)
+    kl = torch.randint(80, Tt + 1, (Bw,), generator=g); kl[0] = Tt
+    for _ in range(2):
+        G.attention_bwd(q, km, vm, do, ql, kl, H, False)                              # cross-attention backward
 print("done")

@@ -15,7 +15,8 @@ if os.path.exists(path):
     rows = list(csv.DictReader(lines))
     # keep only one inference step: the launches between the first and second embed_kernel
     idx = [i for i, r in enumerate(rows) if "embed_kernel" in r["Kernel Name"]]
-    step = rows[idx[-2]:idx[-1]] if len(idx) >= 2 else rows
+    # dual-chain inference: the batch is split in two halves that run as two launch chains -> two embed kernels per step
+    step = rows[idx[-3]:idx[-1]] if len(idx) >= 3 else rows
     for r in step:
         name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").replace("vb::", "")
         key = (name, r["Grid Size"], r["Block Size"])
@@ -29,7 +30,8 @@ if os.path.exists(path):
         f.write(f"# ncu launch list, one VAENAR.inference step at C2 (B16, T_text 148, T_mel 870) -- {ROUND}\n\n")
         f.write("`ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 1`; "
                 "per-launch times are cold-cache and serialised, so compare SHARES, not absolutes.\n\n")
-        f.write(f"{len(step)} launches, {tot:.0f} us summed device time.\n\n| kernel | grid | block | launches | total us | avg us | share |\n|---|---|---|---|---|---|---|\n")
+        f.write(f"{len(step)} launches (both launch chains of the step: batch halves 8 + 8 run concurrently on two streams; ncu "
+                f"serialises them), {tot:.0f} us summed device time.\n\n| kernel | grid | block | launches | total us | avg us | share |\n|---|---|---|---|---|---|---|\n")
         for (name, grid, blk), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| {name} | {grid} | {blk} | {n} | {t:.1f} | {t / n:.1f} | {t / tot:.3f} |\n")
         by = collections.defaultdict(float)
@@ -39,6 +41,32 @@ if os.path.exists(path):
         for k, t in sorted(by.items(), key=lambda kv: -kv[1]):
             f.write(f"| {k} | {t:.1f} | {t / tot:.3f} |\n")
     print("wrote launches summary:", len(step), "launches", f"{tot:.0f} us")
+
+# ---- 1b. launch list of one train_step (tools/ncu_train.py under ncu --profile-from-start off)
+path = os.path.join(GO, f"launches_train_{ROUND}.csv")
+if os.path.exists(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    rows = list(csv.DictReader(lines))
+    agg = collections.OrderedDict()
+    for r in rows:
+        name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").replace("vb::", "")
+        if "at::" in name:
+            name = "torch:" + re.sub(r"<.*", "", name).split("::")[-1]
+        v = float(r["Metric Value"].replace(",", ""))
+        v = v / 1e3 if r["Metric Unit"] == "ns" else (v * 1e3 if r["Metric Unit"] == "ms" else v)
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    with open(os.path.join(OUT, f"launches_train_{ROUND}.md"), "w") as f:
+        f.write(f"# ncu launch list, one train_step at C3 (B32, T_text 148, T_mel 870, rf 2) -- {ROUND}\n\n"
+                "`ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none python tools/ncu_train.py 32 2` "
+                "(forward with tape + backward + Adam + operand re-pack; the weight-gradient stream is serialised by ncu). "
+                "Per-launch times are cold-cache and serialised: compare SHARES.\n\n")
+        f.write(f"{len(rows)} launches, {tot:.0f} us summed device time.\n\n| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|\n")
+        for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| {name} | {n} | {t:.1f} | {t / n:.1f} | {t / tot:.3f} |\n")
+    print("wrote train launch summary:", len(rows), "launches", f"{tot:.0f} us")
 
 # ---- 2. full-set captures -> key metrics per kernel
 WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
@@ -62,17 +90,22 @@ def to_bytes(v, unit):
 
 
 traffic = {}
+KREG = {"attn": "attention_tc", "gemm": "gemm_tc", "wgrad": "wgrad_tc", "attn_bwd": "attn_bwd_d"}
 for tag, labels in (("attn", ["self-attention causal (B16,H4,Tq=Tk=435)"] * 2 + ["cross-attention (Tq 435, Tk 148)"] * 2 +
                       ["decoder cross-attention with alignments output (Tq 435, Tk 148)"]),
                     ("gemm", ["FFN dense1 + bias + relu (M6960,K256,N1024), BLOCK_N 128"] * 2 +
-                     ["FFN dense2 + bias + residual + LayerNorm (M6960,K1024,N256), BLOCK_N 256 single CTA"] * 2)):
+                     ["FFN dense2 + bias + residual + LayerNorm (M6960,K1024,N256), BLOCK_N 256 single CTA"] * 2),
+                    ("wgrad", ["FFN dense1 weight gradient dW[256,1024] over 13920 tokens (C3)"] * 2 +
+                     ["att_proj weight gradient dW[512,256] ([x ; ctx] concat) over 13920 tokens"] * 2),
+                    ("attn_bwd", ["causal self-attention backward (B32,H4,T435): dK/dV kernel", "same: dQ kernel"] * 2 +
+                     ["cross-attention backward (Tq 435, Tk 148): dK/dV kernel", "same: dQ kernel"] * 2)):
     rep = os.path.join(GO, f"prof_{tag}_{ROUND}.ncu-rep")
     if not os.path.exists(rep):
         continue
     hdr, units, rows = raw(rep)
     with open(os.path.join(OUT, f"{tag}_{ROUND}.md"), "w") as f:
         f.write(f"# ncu --set full --clock-control none: {tag} kernels at C2 shapes -- {ROUND}\n\n"
-                f"`ncu --set full --clock-control none --import-source on -k regex:{'attention_tc' if tag == 'attn' else 'gemm_tc'} "
+                f"`ncu --set full --clock-control none --import-source on -k regex:{KREG[tag]} "
                 f"python tools/prof_kernels.py {tag}` (block-level C-ABI hooks, same kernels/shapes as the model).\n")
         for k, r in enumerate(rows):
             name = r[hdr.index("Kernel Name")]
@@ -93,7 +126,20 @@ for tag, labels in (("attn", ["self-attention causal (B16,H4,Tq=Tk=435)"] * 2 + 
                 traffic["attn_cross"] = dr + dw
             if tag == "attn" and k == 4:
                 traffic["attn_cross_ali"] = dr + dw
+            if tag == "wgrad" and k == 1:
+                traffic["wgrad"] = dr + dw
+            if tag == "attn_bwd" and k == 2:
+                traffic["attn_bwd_dkdv_self"] = dr + dw
+            if tag == "attn_bwd" and k == 3:
+                traffic["attn_bwd_dq_self"] = dr + dw
     print("wrote", tag)
 if traffic:
+    old = {}
+    try:
+        old = json.load(open(os.path.join(OUT, "traffic.json")))
+    except Exception:
+        pass
+    old.update(traffic)
+    traffic = old
     json.dump(traffic, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
     print(traffic)
