@@ -364,7 +364,7 @@ def run_train(args):
     if rank == 0:
         pk = peaks()
         lib.vaenar_profile_enable(1)
-        step_dev()
+        model.train_step_grads(d_texts, d_mels, d_t, d_m, klw, rf)      # local pass: no collective on this rank alone
         rep = json.loads(lib.vaenar_profile_report().decode())
         lib.vaenar_profile_enable(0)
         tot_ms = sum(v["ms"] for v in rep.values()) or 1.0
