@@ -15,7 +15,7 @@ namespace vb {
 // The forward saves y and rstd only; xhat = (y - beta) / gamma is reconstructed (gamma != 0; |gamma| < 1e-20 -> xhat = 0).
 //   du = rstd * (gamma*dy - mean_j(gamma*dy) - xhat * mean_j(gamma*dy*xhat))
 // Also: dgamma += sum_rows dy*xhat, dbeta += sum_rows dy, dbias += sum_rows du (bias of the Dense feeding the LN).
-// One warp per row, 64 rows per CTA; du may alias dy.
+// One warp per row, 32 rows per CTA; du may alias dy.
 template <int D>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* dy, const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -37,8 +37,8 @@ ln_bwd_kernel(const float* dy, const float* __restrict__ y, const float* __restr
   for (int j = 0; j < NJ; ++j)
 #pragma unroll
     for (int e = 0; e < 4; ++e) ag[j][e] = ab[j][e] = au[j][e] = 0.f;
-  const long r0 = static_cast<long>(blockIdx.x) * 64;
-  for (int rr = warp; rr < 64; rr += 8) {
+  const long r0 = static_cast<long>(blockIdx.x) * 32;
+  for (int rr = warp; rr < 32; rr += 8) {
     const long row = r0 + rr;
     if (row >= rows) break;
     float d[NJ][4], xh[NJ][4];

@@ -118,7 +118,10 @@ struct vaenar_model {
   std::map<std::string, int64_t> pvecs;   // fp32 vectors in the packed arena (byte offsets)
   std::vector<PackPlanOp> plan;
   int64_t packed_bytes = 0;
-  int64_t off_packops = 0, off_ptrs = 0, off_logdet64 = 0, off_winv = 0;
+  int64_t off_packops = 0, off_packtiles = 0, off_ptrs = 0, off_logdet64 = 0, off_winv = 0;
+  std::vector<int> host_tiles;          // first CTA of every pack op (prefix sums)
+  cudaEvent_t ev_flow_ready = nullptr;  // the flow constants (W^-1, log|det W|, folded maps) are produced on the side stream
+  bool flow_pending = false;
   int64_t off_Mf = 0, off_cf = 0, off_Mb = 0, off_cb = 0, off_consts = 0;
   std::vector<PackOp> host_ops;
   std::vector<const float*> host_ptrs;
@@ -519,6 +522,7 @@ static void build_model(vaenar_model& m) {
   m.off_logdet64 = region(S * 8);
   m.off_ptrs = region(3 * S * 8);
   m.off_packops = region(static_cast<int64_t>(m.plan.size()) * sizeof(PackOp));
+  m.off_packtiles = region(static_cast<int64_t>(m.plan.size() + 1) * sizeof(int));
   m.packed_bytes = align_up(m.packed_bytes, 1024);
 }
 
@@ -1324,7 +1328,8 @@ static void prior_sample(Ctx& c, const float* text_embd, const int* t_len, const
   const int64_t mark = c.ws_off;
   PriorBufs b = prior_setup(c, text_embd, B, Tt, Tz);
   if (!c.dry) {
-    base_logprob_kernel<<<B, 256, 0, c.stream>>>(z, z_len, b.base, Tz, L);
+    VB_CUDA(cudaMemsetAsync(b.base, 0, B * sizeof(float), c.stream));
+    base_logprob_kernel<<<dim3(B, 16), 256, 0, c.stream>>>(z, z_len, b.base, Tz, L);
     check_launch("base_logprob");
   }
   const float* Mf = c.dry ? nullptr : reinterpret_cast<const float*>(c.packed + c.m->off_Mf);
@@ -1388,7 +1393,8 @@ static void prior_logprob(Ctx& c, const float* z_in, const float* text_embd, con
     flow_linear(c, z, b.zh, c.dry ? nullptr : Mb + static_cast<int64_t>(s) * L * L, c.dry ? nullptr : cb + s * L, rows);
   }
   if (!c.dry) {
-    base_logprob_kernel<<<B, 256, 0, c.stream>>>(z, z_len, b.base, Tz, L);
+    VB_CUDA(cudaMemsetAsync(b.base, 0, B * sizeof(float), c.stream));
+    base_logprob_kernel<<<dim3(B, 16), 256, 0, c.stream>>>(z, z_len, b.base, Tz, L);
     check_launch("base_logprob");
     // backward log-dets: coupling -sum log scale (already signed in row_acc), linear -len*log|det W|, actnorm -len*sum s
     prior_logp_finalize_kernel<<<B, 256, 0, c.stream>>>(b.base, b.row_acc,
@@ -1660,6 +1666,7 @@ static void init_fwd(Ctx& c, const int* texts, const int* t_len, const int* z_le
   c.ws_off = mark;
 }
 
+static void join_flow(Ctx& c);
 #include "train.inc"
 
 // ============================================================================ weight packing
@@ -1684,11 +1691,14 @@ static void pack_weights(vaenar_model* m, const float* params, uint8_t* packed, 
   PackOp* dops = reinterpret_cast<PackOp*>(packed + m->off_packops);
   VB_CUDA(cudaMemcpyAsync(dops, m->host_ops.data(), m->host_ops.size() * sizeof(PackOp), cudaMemcpyHostToDevice, stream));
   const int nops = static_cast<int>(m->host_ops.size());
-  for (int o0 = 0; o0 < nops; o0 += 65535) {
-    dim3 grid(cdiv(maxN, 32), cdiv(maxK, 32), std::min(65535, nops - o0));
-    pack_weights_kernel<<<grid, dim3(32, 8), 0, stream>>>(dops + o0);
-    check_launch("pack_weights");
-  }
+  m->host_tiles.assign(nops + 1, 0);
+  for (int i = 0; i < nops; ++i)
+    m->host_tiles[i + 1] = m->host_tiles[i] + cdiv(m->host_ops[i].N, 32) * cdiv(m->host_ops[i].K, 32);
+  int* dtiles = reinterpret_cast<int*>(packed + m->off_packtiles);
+  VB_CUDA(cudaMemcpyAsync(dtiles, m->host_tiles.data(), (nops + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+  pack_weights_flat_kernel<<<m->host_tiles[nops], dim3(32, 8), 0, stream>>>(dops, dtiles, nops);
+  check_launch("pack_weights");
+  (void)maxK; (void)maxN;
   auto PP = [&](const std::string& n) { return params + m->params[m->P(n)].offset; };
   auto VV = [&](const std::string& n) { return reinterpret_cast<float*>(packed + m->pvecs.at(n)); };
   // 2. inference BatchNorm -> affine
@@ -1722,6 +1732,20 @@ static void pack_weights(vaenar_model* m, const float* params, uint8_t* packed, 
   }
   const float** dptrs = reinterpret_cast<const float**>(packed + m->off_ptrs);
   VB_CUDA(cudaMemcpyAsync(dptrs, m->host_ptrs.data(), 3 * S * sizeof(float*), cudaMemcpyHostToDevice, stream));
+  // The 128x128 LU / inverse kernels are latency-bound single-CTA work: run them on the side stream so that they
+  // overlap the operand packing and whatever the caller launches next; consumers join through ev_flow_ready.
+  cudaStream_t main_stream = stream;
+  if (!m->wgrad_stream) VB_CUDA(cudaStreamCreateWithFlags(&m->wgrad_stream, cudaStreamNonBlocking));
+  if (!m->ev_flow_ready) VB_CUDA(cudaEventCreateWithFlags(&m->ev_flow_ready, cudaEventDisableTiming));
+  {
+    if (!m->ev_fork) {
+      VB_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+      VB_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    }
+    VB_CUDA(cudaEventRecord(m->ev_fork, main_stream));
+    VB_CUDA(cudaStreamWaitEvent(m->wgrad_stream, m->ev_fork, 0));
+    stream = m->wgrad_stream;
+  }
   double* ld64 = reinterpret_cast<double*>(packed + m->off_logdet64);
   float* winv = reinterpret_cast<float*>(packed + m->off_winv);
   slogdet128_kernel<<<S, FLOW_DIM, FLOW_DIM * (FLOW_DIM + 1) * 8, stream>>>(dptrs, ld64);
@@ -1733,6 +1757,14 @@ static void pack_weights(vaenar_model* m, const float* params, uint8_t* packed, 
                                               reinterpret_cast<float*>(packed + m->off_cb),
                                               reinterpret_cast<float*>(packed + m->off_consts));
   check_launch("flow prepare");
+  VB_CUDA(cudaEventRecord(m->ev_flow_ready, stream));
+  m->flow_pending = true;
+}
+// order the flow constants produced by the last pack_weights before what follows on c.stream
+static void join_flow(Ctx& c) {
+  if (c.dry || !c.m || !c.m->flow_pending) return;
+  VB_CUDA(cudaStreamWaitEvent(c.stream, c.m->ev_flow_ready, 0));
+  c.m->flow_pending = false;
 }
 
 // ============================================================================ C ABI
@@ -1749,7 +1781,8 @@ static void pack_weights(vaenar_model* m, const float* params, uint8_t* packed, 
   }                                      \
   return 0;
 
-static Ctx make_ctx(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes, void* stream) {
+static Ctx make_ctx(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes, void* stream,
+                    bool defer_flow_join = false) {
   if (!h) VB_THROW("null handle");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) VB_THROW("no CUDA device: the B200 path has no CPU fallback");
@@ -1757,6 +1790,7 @@ static Ctx make_ctx(vaenar_handle_t h, const float* params, const void* packed, 
   Ctx c;
   c.m = h; c.params = params; c.packed = const_cast<uint8_t*>(static_cast<const uint8_t*>(packed));
   c.ws = static_cast<uint8_t*>(ws); c.ws_bytes = ws_bytes; c.stream = static_cast<cudaStream_t>(stream);
+  if (!defer_flow_join) join_flow(c);
   return c;
 }
 
@@ -1781,6 +1815,7 @@ int vaenar_create(const vaenar_hparams_t* hps, vaenar_handle_t* out) {
 }
 int vaenar_destroy(vaenar_handle_t h) {
   if (h) {
+    if (h->ev_flow_ready) cudaEventDestroy(h->ev_flow_ready);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->wgrad_stream) cudaStreamDestroy(h->wgrad_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1956,7 +1991,7 @@ int vaenar_train_step_grads(vaenar_handle_t h, float* params, const void* packed
   API_BEGIN
   if (!grads || !losses) VB_THROW("null gradient / loss buffer");
   if (!(loss_scale > 0.f)) VB_THROW("loss_scale must be positive");
-  Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
+  Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream, /*defer_flow_join=*/true);   // joined right before the prior
   apply_train_opts(c, params, opts);
   if (!getenv("VAENAR_NO_WGRAD_STREAM")) {
     if (!h->wgrad_stream) VB_CUDA(cudaStreamCreateWithFlags(&h->wgrad_stream, cudaStreamNonBlocking));

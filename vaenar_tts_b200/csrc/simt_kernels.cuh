@@ -45,6 +45,41 @@ __global__ void pack_weights_kernel(const PackOp* __restrict__ ops) {
   }
 }
 
+// Same, one CTA per 32x32 tile of the whole plan: tile_start[op] = first CTA of op (prefix sums, nops + 1 entries)
+__global__ void pack_weights_flat_kernel(const PackOp* __restrict__ ops, const int* __restrict__ tile_start, int nops) {
+  int lo = 0, hi = nops - 1;
+  const int b = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_start[mid] <= b) lo = mid; else hi = mid - 1;
+  }
+  const PackOp op = ops[lo];
+  const int t = b - tile_start[lo];
+  const int tn = (op.N + 31) / 32;
+  const int n0 = (t % tn) * 32, k0 = (t / tn) * 32;
+  __shared__ float tile[32][33];
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < op.K && n < op.N) ? op.src[static_cast<long>(k) * op.lds + n] : 0.f;
+  }
+  __syncthreads();
+  if (op.mode == 2) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int k = k0 + i, n = n0 + threadIdx.x;
+      if (k < op.K && n < op.N) op.dst[static_cast<long>(k) * op.ldd + n] = __float2half_rn(tile[i][threadIdx.x]);
+    }
+    return;
+  }
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    if (n < op.N && k < op.K) {
+      const float v = tile[threadIdx.x][i];
+      const __half hi16 = __float2half_rn(v);
+      op.dst[static_cast<long>(n) * op.ldd + k] = op.mode ? __float2half_rn(v - __half2float(hi16)) : hi16;
+    }
+  }
+}
+
 // Inference-mode BatchNorm folded to a per-channel affine (modules/utils.py:72; Keras eps 1e-3):
 //   y = (x - mean) * rsqrt(var + eps) * gamma + beta  =  x * scale + shift
 __global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
@@ -152,6 +187,30 @@ __global__ void length_predictor_kernel(const float* __restrict__ x, const float
 // ------------------------------------------------------------------ flow linear algebra (DIM = 128)
 constexpr int FLOW_DIM = 128;
 
+// Partial-pivot search of column k over rows k..127 by warp 0 (first maximum wins, like the serial scan).
+template <typename T>
+__device__ __forceinline__ void pivot_search(const T* A, int ld, int k, int* piv, T* pivval) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    T bv = static_cast<T>(-1);
+    int best = FLOW_DIM;
+    for (int i = k + lane; i < FLOW_DIM; i += 32) {
+      const T v = A[i * ld + k] < static_cast<T>(0) ? -A[i * ld + k] : A[i * ld + k];
+      if (v > bv) { bv = v; best = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const T ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best, o);
+      if (ov > bv || (ov == bv && oi < best)) { bv = ov; best = oi; }
+    }
+    if (lane == 0) {
+      *piv = best;
+      if (pivval) *pivval = bv;
+    }
+  }
+}
+
 // log|det W| in float64 with partial pivoting (modules/flow.py:126-129: slogdet(cast(W, float64))).
 // One CTA of 128 threads per matrix; thread j owns column j.
 __global__ void slogdet128_kernel(const float* const* __restrict__ Ws, double* __restrict__ out) {
@@ -165,16 +224,7 @@ __global__ void slogdet128_kernel(const float* const* __restrict__ Ws, double* _
   __syncthreads();
   double logdet = 0.0;
   for (int k = 0; k < FLOW_DIM; ++k) {
-    if (j == 0) {
-      int best = k;
-      double bv = fabs(A[k * LD + k]);
-      for (int i = k + 1; i < FLOW_DIM; ++i) {
-        const double v = fabs(A[i * LD + k]);
-        if (v > bv) { bv = v; best = i; }
-      }
-      piv = best;
-      pivval = bv;
-    }
+    pivot_search<double>(A, LD, k, &piv, &pivval);
     __syncthreads();
     const int pr = piv;
     if (pr != k) {
@@ -209,15 +259,7 @@ __global__ void inverse128_kernel(const float* const* __restrict__ Ws, float* __
     G[i * LD + j] = j < FLOW_DIM ? W[i * FLOW_DIM + j] : ((j - FLOW_DIM) == i ? 1.f : 0.f);
   __syncthreads();
   for (int k = 0; k < FLOW_DIM; ++k) {
-    if (j == 0) {
-      int best = k;
-      float bv = fabsf(G[k * LD + k]);
-      for (int i = k + 1; i < FLOW_DIM; ++i) {
-        const float v = fabsf(G[i * LD + k]);
-        if (v > bv) { bv = v; best = i; }
-      }
-      piv = best;
-    }
+    pivot_search<float>(G, LD, k, &piv, static_cast<float*>(nullptr));
     __syncthreads();
     const int pr = piv;
     if (pr != k) {
@@ -337,12 +379,15 @@ __global__ void base_logprob_kernel(const float* __restrict__ e, const int* __re
   const long n = static_cast<long>(len) * D;
   const float* base = e + static_cast<long>(b) * T * D;
   float acc = 0.f;
-  for (long i = threadIdx.x; i < n; i += blockDim.x) {
+  for (long i = static_cast<long>(blockIdx.y) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.y) * blockDim.x) {
     const float v = base[i];
     acc += -0.5f * (1.8378770664093453f + v * v);
   }
   const float tot = block_sum(acc, sh);
-  if (threadIdx.x == 0) out[b] = tot;
+  if (threadIdx.x == 0) {
+    if (gridDim.y == 1) out[b] = tot;
+    else atomicAdd(out + b, tot);   // out zeroed by the caller
+  }
 }
 
 // logp[b] = base[b] + sign * ( sum_rows row_acc  +  len_b * sum_steps (sum_s + logdetW) )
