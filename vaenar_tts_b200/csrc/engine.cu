@@ -645,6 +645,8 @@ static void set_attrs(vaenar_model* m) {
   VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_DKDV_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_DQ_SMEM));
+  VB_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB2_DKDV_SMEM));
+  VB_CUDA(cudaFuncSetAttribute(attn_bwd_dq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB2_DQ_SMEM));
   VB_CUDA(cudaFuncSetAttribute(flow_param_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (2 * FLOW_DIM * (FLOW_DIM + 1) + FLOW_DIM) * 4));
   VB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
@@ -940,9 +942,10 @@ static void run_attention_bwd(Ctx& c, int B, int H, const AttnBwdCall& a) {
   const CUtensorMap tV = make_tmap(a.v, 3, a.v_ld, a.Tk, B, a.v_ld, static_cast<uint64_t>(a.Tk) * a.v_ld, 64, 128);
   const CUtensorMap tO = make_tmap(a.dO, 3, a.do_ld, a.Tq, B, a.do_ld, static_cast<uint64_t>(a.Tq) * a.do_ld, 64, 128);
   const double work = static_cast<double>(B) * H * a.Tq * a.Tk;
+  static const bool v1 = getenv("VAENAR_ATTN_BWD_V1") != nullptr;   // 128-wide tiles, one CTA per SM (kept for A/B timing)
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.blockDim = dim3(ATB_THREADS);
+  cfg.blockDim = dim3(v1 ? ATB_THREADS : ATB2_THREADS);
   cfg.stream = c.stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -953,8 +956,11 @@ static void run_attention_bwd(Ctx& c, int B, int H, const AttnBwdCall& a) {
     ProfileScope prof(a.causal ? "attn_bwd_dkdv_self" : "attn_bwd_dkdv_cross", 8.0 * work * ATT_D,
                       static_cast<double>(B) * H * ATT_D * 2 * (2.0 * a.Tq + 4.0 * a.Tk), c.stream);
     cfg.gridDim = dim3(cdiv(a.Tk, 128), H, B);
-    cfg.dynamicSmemBytes = ATB_DKDV_SMEM;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, attn_bwd_dkdv_kernel, tQ, tK, tV, tO, p);
+    cfg.dynamicSmemBytes = v1 ? ATB_DKDV_SMEM : ATB2_DKDV_SMEM;
+    const CUtensorMap tQ64 = make_tmap(a.q, 3, a.q_ld, a.Tq, B, a.q_ld, static_cast<uint64_t>(a.Tq) * a.q_ld, 64, 64);
+    const CUtensorMap tO64 = make_tmap(a.dO, 3, a.do_ld, a.Tq, B, a.do_ld, static_cast<uint64_t>(a.Tq) * a.do_ld, 64, 64);
+    const cudaError_t le = v1 ? cudaLaunchKernelEx(&cfg, attn_bwd_dkdv_kernel, tQ, tK, tV, tO, p)
+                              : cudaLaunchKernelEx(&cfg, attn_bwd_dkdv2_kernel, tQ64, tK, tV, tO64, p);
     if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(attn_bwd_dkdv_kernel) failed: %s", cudaGetErrorString(le));
     check_launch("attn_bwd_dkdv_kernel");
   }
@@ -962,8 +968,11 @@ static void run_attention_bwd(Ctx& c, int B, int H, const AttnBwdCall& a) {
     ProfileScope prof(a.causal ? "attn_bwd_dq_self" : "attn_bwd_dq_cross", 6.0 * work * ATT_D,
                       static_cast<double>(B) * H * ATT_D * 2 * (3.0 * a.Tq + 2.0 * a.Tk), c.stream);
     cfg.gridDim = dim3(cdiv(a.Tq, 128), H, B);
-    cfg.dynamicSmemBytes = ATB_DQ_SMEM;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, attn_bwd_dq_kernel, tQ, tK, tV, tO, p);
+    cfg.dynamicSmemBytes = v1 ? ATB_DQ_SMEM : ATB2_DQ_SMEM;
+    const CUtensorMap tK64 = make_tmap(a.k, 3, a.k_ld, a.Tk, B, a.k_ld, static_cast<uint64_t>(a.Tk) * a.k_ld, 64, 64);
+    const CUtensorMap tV64 = make_tmap(a.v, 3, a.v_ld, a.Tk, B, a.v_ld, static_cast<uint64_t>(a.Tk) * a.v_ld, 64, 64);
+    const cudaError_t le = v1 ? cudaLaunchKernelEx(&cfg, attn_bwd_dq_kernel, tQ, tK, tV, tO, p)
+                              : cudaLaunchKernelEx(&cfg, attn_bwd_dq2_kernel, tQ, tK64, tV64, tO, p);
     if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(attn_bwd_dq_kernel) failed: %s", cudaGetErrorString(le));
     check_launch("attn_bwd_dq_kernel");
   }
