@@ -1,4 +1,5 @@
-"""Tiny run of every C-ABI path (inference, call eval, call training-forward, init) for compute-sanitizer."""
+"""Tiny run of every C-ABI path (inference, call eval, call training-forward, init, two full train_steps) for
+compute-sanitizer."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,4 +13,6 @@ mel, ali = m.inference(texts, m_len, t_len, reduction_factor=2)
 out = m(inputs=texts, mel_targets=mels, mel_lengths=m_len, text_lengths=t_len, reduction_factor=2, training=False, reduce_loss=True)
 out2 = m(inputs=texts, mel_targets=mels, mel_lengths=m_len, text_lengths=t_len, reduction_factor=2, training=True, reduce_loss=True)
 m.init(texts, m_len, t_len)
-torch.cuda.synchronize(); print("ok", float(mel.abs().mean()), float(out[2]))
+for _ in range(2):
+    loss = m.train_step(texts, mels, t_len, m_len, 1e-5, 2)
+torch.cuda.synchronize(); print("ok", float(mel.abs().mean()), float(out[2]), float(loss[0]))
