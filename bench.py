@@ -301,16 +301,20 @@ def run_train(args):
         ge.build()
     if world > 1:
         dist.barrier()
-    from vaenar_tts_b200 import VAENAR, LJHPS, _lib
+    from vaenar_tts_b200 import VAENAR, LJHPS, DataBakerHPS, _lib
     lib = _lib.load()
     from oracle.vaenar_oracle import synthetic_batch
-    from oracle.hparams import LJHPS as OH
-    B, Tt, Tm, rf = args.train_batch, T_TEXT, T_MEL, RF
+    from oracle.hparams import LJHPS as OLJ, DataBakerHPS as ODB
+    c4 = args.workload == "c4"
+    # C4 (BASELINE.json configs[3]): DataBaker hparams, global batch 64 = 16 per GPU on 4 GPUs; BASELINE.json names no
+    # sequence shape, SURVEY.md 8d proposes T_text 152 / T_mel 640.
+    OH, HPS = (ODB, DataBakerHPS) if c4 else (OLJ, LJHPS)
+    B, Tt, Tm, rf = (args.train_batch if not c4 else 16), (152 if c4 else T_TEXT), (640 if c4 else T_MEL), RF
     dev = f"cuda:{local}"
     texts, mels, t_len, m_len = synthetic_batch(OH, B, Tt, Tm, seed=OH.Train.random_seed + rank)
     h_texts, h_mels = texts.pin_memory(), mels.pin_memory()
     d_texts, d_mels, d_t, d_m = (x.to(dev) for x in (texts, mels, t_len, m_len))
-    model = VAENAR(LJHPS, device=dev, seed=OH.Train.random_seed)
+    model = VAENAR(HPS, device=dev, seed=OH.Train.random_seed)
     model.init(d_texts, d_m, d_t)                       # init_step of train.py:172-179 (data-dependent ActNorm)
     klw = float(OH.Train.kl_weight_init) if hasattr(OH.Train, "kl_weight_init") else 1e-5
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -373,7 +377,11 @@ def run_train(args):
                    for k, v in rep.items() if v["ms"] > 0}
         dom = max(rep, key=lambda k: rep[k]["ms"])
         achieved = classes[dom]["tflops"]
-        flops_per_frame = 91.66e6           # C3 train step (fwd + bwd = 3 x fwd), rf = 2
+        # SURVEY.md 8d algorithmic FLOPs of one train step (fwd + bwd = 3 x fwd, rf = 2), per mel frame
+        Tz = (Tm + rf - 1) // rf
+        xblk = Tz * (1048576 + 512 * (Tz + Tt)) + Tt * 262144
+        mac = Tt * (11534336 + 2048 * Tt) + 16 * xblk + Tz * (151552 + 6 * 65536 + 135168) + Tz * rf * 1433600
+        flops_per_frame = 6.0 * mac / Tm
         step_tflops = flops_per_frame * B * Tm / (ms_dev / args.steps * 1e-3) / 1e12
         line = {
             "metric": "mel-frames/sec", "value": frames_total / (ms_dev / 1e3), "unit": "frames/s", "n_gpus": world,
@@ -381,8 +389,8 @@ def run_train(args):
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands / f32 accumulate (residual streams, LN/BN/softmax statistics, flow, Adam in f32)",
             "data": "synthetic",
-            "config": {"workload": f"C3: LJSpeech hparams, batch={B}/GPU, T_text={Tt}, T_mel={Tm}, full train_step "
-                       "(encoder + posterior + prior flow + decoder + KL, backward, Adam), rf=2", "batch_per_gpu": B,
+            "config": {"workload": f"{'C4: DataBaker' if c4 else 'C3: LJSpeech'} hparams, batch={B}/GPU, T_text={Tt}, T_mel={Tm}, "
+                       "full train_step (encoder + posterior + prior flow + decoder + KL, backward, Adam), rf=2", "batch_per_gpu": B,
                        "parallelism": f"dp{world} (one NCCL all-reduce of the flat gradient buffer)" if world > 1 else "single GPU",
                        "l2": "flushed between timed steps", "execution": "eager C-ABI launch sequence"},
             "e2e": {"value": frames_total / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
@@ -408,13 +416,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs only)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
-                    help="c2 (default, the BASELINE.json metric): inference; c3: full train_step")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+                    help="c2 (default, the BASELINE.json metric): inference; c3: full train_step (LJSpeech, B32/GPU); "
+                         "c4: full train_step, DataBaker hparams, B16/GPU (run with --gpus 4 for the named config)")
     ap.add_argument("--train-batch", type=int, default=32, help="per-GPU batch of the c3 workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "c3":
+    elif args.workload in ("c3", "c4"):
         run_train(args)
     else:
         run_ours(args)
