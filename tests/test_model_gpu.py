@@ -205,3 +205,28 @@ def test_session_graph_matches_eager():
     torch.cuda.synchronize()
     mel, _ = m.inference(texts, m_len, t_len, reduction_factor=2, epsilon=sess.eps.clone(), return_alignments=False)
     assert float((h_mel - mel.cpu()).abs().max()) == 0.0
+
+
+def test_inference_py_test_step_vs_oracle():
+    """inference.py:125-143: predicted lengths (+80 frames), temperature-0 prior sample, decoder at rf=2"""
+    P = O.init_params(OLJ, seed=31, zero_init_std=0.02)
+    O.randomize_bn_stats(P, seed=32)
+    P["length_predictor.projection.bias"] = torch.tensor([1.2])          # e^1.2 ~ 3.3 frames per phoneme
+    m = make_model(OLJ, P)
+    texts, _, t_len, _ = O.synthetic_batch(OLJ, 3, 30, 120, seed=33)
+    mel, lens, ali = m.test_step(texts, t_len, temperature=0.0)
+    with torch.no_grad():
+        emb = O.text_encoder(P, OLJ, texts, t_len, OLJ.Common.mel_text_len_ratio / 2.0)
+        pred_f = O.length_predictor(P, emb, t_len)
+        # float -> int32 truncation can legitimately differ by one frame at an integer boundary: the float predictions
+        # must agree, and the oracle continues from the lengths the CUDA path chose
+        assert int((lens.cpu() - 80 - pred_f.to(torch.int32)).abs().max()) <= 1
+        assert rel(m.length_predictor(m.text_encoder(texts, t_len, pos_step=OLJ.Common.mel_text_len_ratio / 2.0), t_len),
+                   pred_f) < 1e-3
+        reduced = (lens.cpu() + 1) // 2
+        eps = torch.zeros(3, int(reduced.max()), 128)
+        z, _ = O.prior_sample(P, OLJ, eps, reduced, emb, t_len)
+        _, ref, ref_ali = O.decoder(P, OLJ, z, emb, reduced, t_len, 2)
+    assert mel.shape == ref.shape
+    assert masked_mae(mel, ref, reduced * 2) <= MEL_MAE_TOL
+    assert set(ali) == {"decoder-attention-0", "decoder-attention-1"}

@@ -339,8 +339,8 @@ class VAENAR:
         return logp
 
     def _prior_init(self, *a, **kw):
-        raise NotImplementedError("prior.init (data-dependent ActNorm initialisation, modules/prior.py:171-186) "
-                                  "belongs to the training path, which is not implemented on the CUDA path yet")
+        raise NotImplementedError("prior.init (modules/prior.py:171-186) is only reachable through VAENAR.init "
+                                  "(models/models.py:212-226), which runs it fused with the encoder / decoder passes")
 
     def _posterior(self, inputs, src_enc, src_lengths=None, target_lengths=None, training=None, eps=None,
                    reduction_factor=None, full_mels=None):
@@ -419,6 +419,25 @@ class VAENAR:
                                          self._stream()))
         self._last = dict(z=z, text_embd=emb, logp=logp)
         return mel, self._ali_dict(ali)
+
+    def test_step(self, t, t_l, temperature=0.0, return_alignments=True):
+        """The ``test_step`` closure of inference.py:125-143 (length-predictor-driven synthesis): encoder -> predicted
+        lengths (truncated to int32, +80 frames of safety margin) -> prior.sample(temperature; the reference default 0.0
+        makes the synthesis deterministic) -> decoder at the final reduction factor.
+        Returns (mel [B, T_z*rf, 80], predicted_mel_lengths + 80 [B] int32, alignments dict)."""
+        rf = int(self.hps.Common.final_reduction_factor)
+        texts = self._i32(t)
+        t_len = self._i32(t_l)
+        emb = self._text_encoder(texts, t_len, pos_step=self.mel_text_len_ratio / float(rf), training=False)
+        pred = self._length_predictor(emb, t_len, training=False)
+        pred_m_l = pred.to(torch.int32)                                     # tf.cast(float -> int32) truncates
+        reduced = (pred_m_l + 80 + rf - 1) // rf
+        z, _ = self._prior_sample(reduced, emb, t_len, training=False, temperature=float(temperature))
+        _, mel, ali = self._decoder(z, emb, reduced, t_len, reduction_factor=rf, training=False,
+                                    return_alignments=return_alignments)
+        return mel, pred_m_l + 80, ali
+
+    synthesize = test_step
 
     def call(self, inputs, mel_targets, mel_lengths, text_lengths=None, reduction_factor=2, training=None,
              reduce_loss=None, eps=None, return_alignments=True, dropout_masks=None, update_bn_stats=True):
