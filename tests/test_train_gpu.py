@@ -182,3 +182,94 @@ def test_training_loop_reduces_loss():
     assert last[0] < 0.8 * first[0], (first, last)
     mel, _ = m.inference(args[0], args[3], args[2], reduction_factor=int(g["rf"]))
     assert torch.isfinite(mel).all()
+
+
+def _random_masks(hps, B, Tt, Tz, rf, gen):
+    def keep(shape, rate):
+        return (torch.rand(shape, generator=gen) >= rate).float() / (1.0 - rate)
+    E, D = hps.Encoder, hps.Decoder
+    sites = [(f"enc.prenet.{i}", (B, Tt, 512), 0.1) for i in range(E.n_conv)] + [("enc.pos", (B, Tt, 512), 0.1)]
+    sites += [("post.prenet.1", (B, Tz, 256), 0.5), ("post.prenet.2", (B, Tz, 256), 0.5), ("post.pos", (B, Tz, 256), 0.2)]
+    sites += [(f"dec.postnet.{i}", (B, Tz * rf, 256), 0.2) for i in range(D.post_n_conv)]
+    return [n for n, _, _ in sites], {n: keep(sh, r) for n, sh, r in sites}
+
+
+@pytest.mark.parametrize("B,Tt,Tm,rf", [(1, 7, 23, 5), (2, 33, 130, 4), (3, 12, 64, 1)])
+def test_gradients_edge_shapes(B, Tt, Tm, rf):
+    """single utterance, every reduction factor of the curriculum (hparams.py:250-251) incl. the unused output columns of
+    out_projection for rf < 5 (decoder.py:193: zero gradient), T_mel not a multiple of rf, sequences shorter than a tile"""
+    from oracle.hparams import LJHPS as OLJ
+    P = O.init_params(OLJ, seed=41, zero_init_std=0.02)
+    texts, mels, t_len, m_len = O.synthetic_batch(OLJ, B, Tt, Tm, rf=rf, seed=42)
+    Tz = (Tm + rf - 1) // rf
+    gen = torch.Generator().manual_seed(43)
+    eps = torch.randn(B, 1, Tz, 128, generator=gen)
+    order, masks = _random_masks(OLJ, B, Tt, Tz, rf, gen)
+    import contextlib
+
+    def run(emulate):
+        Pg = {k: v.clone().requires_grad_(O.is_trainable(k)) for k, v in P.items()}
+        with (O.emulate_operand_dtype(torch.float16) if emulate else contextlib.nullcontext()):
+            loss, _, _, _ = O.train_step_loss(Pg, OLJ, texts, mels, t_len, m_len, 1e-5, rf, eps, masks=masks, new_stats={})
+            loss.backward()
+        return loss, {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in Pg.items() if O.is_trainable(k)}
+    loss, ref = run(False)
+    _, ref16 = run(True)
+    m = make_model(OLJ, P)
+    losses, flat = m.train_step_grads(texts, mels, t_len, m_len, 1e-5, rf, eps=eps, dropout_masks=[masks[n] for n in order],
+                                      update_bn_stats=False)
+    torch.cuda.synchronize()
+    S = m._last_loss_scale
+    got = {}
+    for n, shape, off, tr in m._manifest:
+        if tr:
+            numel = 1
+            for d in shape:
+                numel *= d
+            got[n] = (flat[off:off + numel].view(shape) / S).cpu()
+    assert abs(float(losses[0]) - float(loss.detach())) <= 2e-3 * abs(float(loss.detach()))
+    bad, worst = compare(got, ref, ref16)
+    assert not bad, (len(bad), bad[:12], worst)
+    if rf < 5:
+        g = got["decoder.out_projection.kernel"]
+        assert float(g[:, rf * 80:].abs().max()) == 0.0        # columns beyond rf*80 are never used (decoder.py:193)
+
+
+def test_full_size_c3_properties():
+    """BASELINE.json configs[2] (C3: B32, T_text 148, T_mel 870) at full size, size-independent properties:
+    (1) the tape-recording training forward agrees with the plain training-mode forward (same kernels, other buffers);
+    (2) the gradients are linear in the loss scale (no fp16 overflow / underflow of the gradient operands at this size);
+    (3) every gradient tensor is finite and non-zero except the unused out_projection columns."""
+    from oracle.hparams import LJHPS as OLJ
+    B, Tt, Tm, rf = 32, 148, 870, 2
+    P = O.init_params(OLJ, seed=51, zero_init_std=0.02)
+    texts, mels, t_len, m_len = O.synthetic_batch(OLJ, B, Tt, Tm, rf=rf, seed=52)
+    Tz = (Tm + rf - 1) // rf
+    gen = torch.Generator().manual_seed(53)
+    eps = torch.randn(B, 1, Tz, 128, generator=gen)
+    order, masks = _random_masks(OLJ, B, Tt, Tz, rf, gen)
+    ml = [masks[n].cuda() for n in order]
+    m = make_model(OLJ, P)
+    _, l2, kl, ll, _ = m(inputs=texts, mel_targets=mels, mel_lengths=m_len, text_lengths=t_len, reduction_factor=rf, training=True,
+                         reduce_loss=True, eps=eps, dropout_masks=ml, update_bn_stats=False, return_alignments=False)
+    losses, flat = m.train_step_grads(texts, mels, t_len, m_len, 1e-5, rf, eps=eps, dropout_masks=ml, update_bn_stats=False,
+                                      loss_scale=65536.0)
+    g16 = (flat / 65536.0).clone()
+    assert rel(losses[1], l2.cpu()) < 1e-4 and rel(losses[2], kl.cpu()) < 1e-4 and rel(losses[3], ll.cpu()) < 1e-4
+    _, flat = m.train_step_grads(texts, mels, t_len, m_len, 1e-5, rf, eps=eps, dropout_masks=ml, update_bn_stats=False,
+                                 loss_scale=4096.0)
+    g12 = flat / 4096.0
+    assert torch.isfinite(g16).all() and torch.isfinite(g12).all()
+    for n, shape, off, tr in m._manifest:
+        if not tr:
+            continue
+        numel = 1
+        for d in shape:
+            numel *= d
+        a, b = g16[off:off + numel].double(), g12[off:off + numel].double()
+        na = float(a.norm())
+        if n.endswith("postnet.conv_stack.4.conv1d.bias"):
+            continue                                              # mathematically zero (bias straight into BatchNorm)
+        assert na > 0, n
+        if numel > 1:
+            assert float((a - b).norm()) / na < 2e-2, (n, float((a - b).norm()) / na)
