@@ -316,6 +316,9 @@ def run_train(args):
     d_texts, d_mels, d_t, d_m = (x.to(dev) for x in (texts, mels, t_len, m_len))
     model = VAENAR(HPS, device=dev, seed=OH.Train.random_seed)
     model.init(d_texts, d_m, d_t)                       # init_step of train.py:172-179 (data-dependent ActNorm)
+    peer = world > 1 and not args.nccl_allreduce
+    if peer:
+        model.enable_peer_optimizer()                   # gradient exchange + Adam as one kernel over NVLink peer memory
     klw = float(OH.Train.kl_weight_init) if hasattr(OH.Train, "kl_weight_init") else 1e-5
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -391,7 +394,9 @@ def run_train(args):
             "data": "synthetic",
             "config": {"workload": f"{'C4: DataBaker' if c4 else 'C3: LJSpeech'} hparams, batch={B}/GPU, T_text={Tt}, T_mel={Tm}, "
                        "full train_step (encoder + posterior + prior flow + decoder + KL, backward, Adam), rf=2", "batch_per_gpu": B,
-                       "parallelism": f"dp{world} (one NCCL all-reduce of the flat gradient buffer)" if world > 1 else "single GPU",
+                       "parallelism": (f"dp{world} (" + ("reduce-scatter + Adam + all-gather fused in one kernel over NVLink peer "
+                                       "memory" if peer else "one NCCL all-reduce of the flat gradient buffer") + ")")
+                       if world > 1 else "single GPU",
                        "l2": "flushed between timed steps", "execution": "eager C-ABI launch sequence"},
             "e2e": {"value": frames_total / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(h_texts.numel() * 4 + h_mels.numel() * 4), "d2h_bytes_per_step": 16},
@@ -420,6 +425,8 @@ def main():
                     help="c2 (default, the BASELINE.json metric): inference; c3: full train_step (LJSpeech, B32/GPU); "
                          "c4: full train_step, DataBaker hparams, B16/GPU (run with --gpus 4 for the named config)")
     ap.add_argument("--train-batch", type=int, default=32, help="per-GPU batch of the c3 workload")
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="c3/c4, N > 1: NCCL all-reduce + Adam instead of the fused peer-memory optimiser kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

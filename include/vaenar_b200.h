@@ -166,6 +166,23 @@ int vaenar_trainable_mask(vaenar_handle_t h, uint8_t* host_mask);
 int vaenar_adam_step(float* params, const float* grads, float* m, float* v, const uint8_t* trainable_mask, int64_t n,
                      int64_t step, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* Data-parallel variant (one process per GPU, world <= 8): the gradient exchange and the optimiser in ONE kernel over
+ * NVLink peer memory.  peer_params / peer_grads: HOST arrays of `world` device pointers to every replica's flat parameter
+ * / gradient buffer (entry `rank` = the local ones; the others are CUDA-IPC mappings of the peers' buffers).  This rank
+ * reduces the gradient shard [rank * S, (rank+1) * S), S = vaenar_adam_shard_floats(n, world), reading the peers' HBM
+ * directly, applies Keras Adam with ITS shard of the moments (m_shard, v_shard: S floats each -- optimiser state is
+ * sharded across the job) and writes the new parameters into every replica.  grad_scale = 1 / (loss_scale * world).
+ * The caller orders the call between two cross-rank barriers on the stream (all gradients complete before; all peer
+ * writes complete after).  Replaces all_reduce + vaenar_adam_step of the N > 1 train_step (train.py:136-137). */
+int vaenar_enable_peer_access(int peer_device);   /* kernels of the current device may dereference peer_device's memory */
+int vaenar_ipc_export(const void* ptr, void* cuda_ipc_mem_handle_64_bytes_out, int64_t* offset_out);
+int vaenar_ipc_open(const void* cuda_ipc_mem_handle_64_bytes, void** out_ptr);   /* cudaIpcOpenMemHandle on the current device */
+int vaenar_ipc_close(void* ptr);
+int64_t vaenar_adam_shard_floats(int64_t n, int world);
+int vaenar_adam_step_sharded(float* const* peer_params, const float* const* peer_grads, float* m_shard, float* v_shard,
+                             const uint8_t* trainable_mask, int64_t n, int rank, int world, int64_t step, float lr, float beta1,
+                             float beta2, float eps, float grad_scale, void* stream);
+
 /* N(0, stddev) noise from the counter-based generator (replaces tf.random.normal at
  * modules/posterior.py:35 and modules/prior.py:35). */
 int vaenar_randn(float* out, int64_t n, uint64_t seed, uint64_t stream_id, float stddev, void* stream);

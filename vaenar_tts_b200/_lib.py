@@ -63,6 +63,13 @@ _SIGS = {
                                         POINTER(TrainOpts), c_float, c_float, c_float, _P, _P, _P, _P]),
     "vaenar_trainable_mask": (c_int, [_P, _P]),
     "vaenar_adam_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_float, c_float, c_float, c_float, c_float, _P]),
+    "vaenar_enable_peer_access": (c_int, [c_int]),
+    "vaenar_ipc_export": (c_int, [_P, _P, POINTER(c_int64)]),
+    "vaenar_ipc_open": (c_int, [_P, POINTER(c_void_p)]),
+    "vaenar_ipc_close": (c_int, [_P]),
+    "vaenar_adam_shard_floats": (c_int64, [c_int64, c_int]),
+    "vaenar_adam_step_sharded": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int64, c_float, c_float, c_float, c_float,
+                                         c_float, _P]),
     "vaenar_randn": (c_int, [_P, c_int64, c_uint64, c_uint64, c_float, _P]),
     "vaenar_launch_count": (ctypes.c_long, []),
     "vaenar_profile_enable": (c_int, [c_int]),

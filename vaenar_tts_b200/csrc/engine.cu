@@ -2033,6 +2033,80 @@ int vaenar_adam_step(float* params, const float* grads, float* m, float* v, cons
   API_END
 }
 
+int vaenar_adam_step_sharded(float* const* peer_params, const float* const* peer_grads, float* m_shard, float* v_shard,
+                             const uint8_t* trainable_mask, int64_t n, int rank, int world, int64_t step, float lr, float beta1,
+                             float beta2, float eps, float grad_scale, void* stream) {
+  API_BEGIN
+  if (step < 1) VB_THROW("Adam step counts from 1");
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) VB_THROW("sharded Adam: rank %d / world %d (max 8)", rank, world);
+  if (n % 4) VB_THROW("sharded Adam: the flat buffer length must be a multiple of 4");
+  const int64_t chunk = (n / 4 + world - 1) / world * 4;
+  const int64_t lo = std::min<int64_t>(n, rank * chunk), hi = std::min<int64_t>(n, lo + chunk);
+  PeerPtrs pp;
+  memset(&pp, 0, sizeof(pp));
+  for (int r = 0; r < world; ++r) { pp.params[r] = peer_params[r]; pp.grads[r] = peer_grads[r]; }
+  const double lr_t = static_cast<double>(lr) * std::sqrt(1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(step))) /
+                      (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(step)));
+  if (hi > lo) {
+    adam_sharded_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(pp, m_shard, v_shard, trainable_mask, lo, hi, rank, world,
+                                                                               static_cast<float>(lr_t), beta1, beta2, eps, grad_scale);
+    check_launch("adam_sharded");
+  }
+  API_END
+}
+int vaenar_enable_peer_access(int peer_device) {
+  API_BEGIN
+  int cur = -1;
+  VB_CUDA(cudaGetDevice(&cur));
+  if (peer_device == cur) return 0;
+  int can = 0;
+  VB_CUDA(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+  if (!can) VB_THROW("device %d cannot access device %d over NVLink / PCIe peer-to-peer", cur, peer_device);
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+  if (e != cudaSuccess) VB_THROW("cudaDeviceEnablePeerAccess(%d) failed: %s", peer_device, cudaGetErrorString(e));
+  API_END
+}
+// Export the cudaMalloc allocation that contains `ptr` for other processes: its cudaIpcMemHandle_t (64 bytes) and the
+// byte offset of `ptr` inside it (PyTorch's caching allocator sub-allocates from large cudaMalloc segments).
+int vaenar_ipc_export(const void* ptr, void* handle64_out, int64_t* offset_out) {
+  API_BEGIN
+  typedef CUresult (*PFN_range)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static PFN_range fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+      VB_THROW("cuMemGetAddressRange unavailable");
+    fn = reinterpret_cast<PFN_range>(p);
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, reinterpret_cast<CUdeviceptr>(ptr)) != CUDA_SUCCESS) VB_THROW("cuMemGetAddressRange failed for %p", ptr);
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base));
+  if (e != cudaSuccess)
+    VB_THROW("cudaIpcGetMemHandle failed (%s): the buffer must come from cudaMalloc (PyTorch: do not use "
+             "PYTORCH_CUDA_ALLOC_CONF=expandable_segments:True)", cudaGetErrorString(e));
+  memcpy(handle64_out, &h, sizeof(h));
+  *offset_out = static_cast<int64_t>(reinterpret_cast<CUdeviceptr>(ptr) - base);
+  API_END
+}
+// Map a peer process's allocation (cudaIpcMemHandle_t, 64 bytes) into THIS device's address space with peer access.
+int vaenar_ipc_open(const void* handle64, void** out_ptr) {
+  API_BEGIN
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  VB_CUDA(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  API_END
+}
+int vaenar_ipc_close(void* ptr) {
+  API_BEGIN
+  VB_CUDA(cudaIpcCloseMemHandle(ptr));
+  API_END
+}
+int64_t vaenar_adam_shard_floats(int64_t n, int world) { return (n / 4 + world - 1) / world * 4; }
+
 int vaenar_randn(float* out, int64_t n, uint64_t seed, uint64_t stream_id, float stddev, void* stream) {
   API_BEGIN
   const int64_t thr = (n + 3) / 4;

@@ -602,6 +602,48 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
   p[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
 
+// Data-parallel optimiser step fused with the gradient exchange over NVLink peer memory (one process per GPU, buffers
+// shared through CUDA IPC).  Rank r owns the parameter shard [lo, hi): it READS the gradient shard of every replica
+// straight from the peers' HBM (reduce-scatter), applies Keras Adam with its shard of the moments, and WRITES the
+// updated parameters into every replica's parameter buffer (all-gather) -- one kernel, no staging buffers, the moments
+// exist only once across the job.  Non-trainable entries (BatchNorm moving statistics: per-replica) are left alone.
+// Ordering against the other ranks' kernels is the caller's job (a barrier before and after).
+struct PeerPtrs {
+  float* params[8];
+  const float* grads[8];
+};
+__global__ void __launch_bounds__(256)
+adam_sharded_kernel(const PeerPtrs pp, float* __restrict__ m, float* __restrict__ v, const uint8_t* __restrict__ trainable,
+                    long lo, long hi, int rank, int world, float lr_t, float b1, float b2, float eps, float grad_scale) {
+  const long n4 = (hi - lo) / 4;
+  for (long j = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; j < n4; j += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long i = lo + j * 4;
+    const uchar4 tm = *reinterpret_cast<const uchar4*>(trainable + i);
+    if (!(tm.x | tm.y | tm.z | tm.w)) continue;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < world; ++r) {
+      const float4 t = *reinterpret_cast<const float4*>(pp.grads[r] + i);
+      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    }
+    float4 p = *reinterpret_cast<const float4*>(pp.params[rank] + i);
+    float4 mi = *reinterpret_cast<const float4*>(m + j * 4);
+    float4 vi = *reinterpret_cast<const float4*>(v + j * 4);
+    float* pe = &p.x; float* me = &mi.x; float* ve = &vi.x; const float* ge = &g.x;
+    const unsigned char te[4] = {tm.x, tm.y, tm.z, tm.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (!te[e]) continue;
+      const float gi = ge[e] * grad_scale;
+      me[e] = b1 * me[e] + (1.f - b1) * gi;
+      ve[e] = b2 * ve[e] + (1.f - b2) * gi * gi;
+      pe[e] -= lr_t * me[e] / (sqrtf(ve[e]) + eps);
+    }
+    *reinterpret_cast<float4*>(m + j * 4) = mi;
+    *reinterpret_cast<float4*>(v + j * 4) = vi;
+    for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(pp.params[r] + i) = p;
+  }
+}
+
 // Inverted-dropout keep mask (Keras Dropout): 0 with probability rate, else 1/(1-rate); same Philox stream layout.
 __global__ void dropout_mask_kernel(float* __restrict__ out, long n, float rate, uint64_t seed, uint64_t stream) {
   const long i4 = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;

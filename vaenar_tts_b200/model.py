@@ -117,6 +117,12 @@ class VAENAR:
 
     def __del__(self):
         try:
+            for base in getattr(self, "_peer_bases", []):
+                self._lib.vaenar_ipc_close(ctypes.c_void_p(base))
+            self._peer_bases = []
+        except Exception:
+            pass
+        try:
             if getattr(self, "_h", None):
                 self._lib.vaenar_destroy(self._h)
         except Exception:
@@ -522,6 +528,69 @@ class VAENAR:
         self._last_loss_scale = S
         return (self._losses, self._grads, mel) if return_mel else (self._losses, self._grads)
 
+    def enable_peer_optimizer(self, group=None):
+        """Data-parallel training over NVLink peer memory: share the flat parameter / gradient buffers of all ranks of
+        ``group`` through CUDA IPC so that train_step can run the gradient exchange and Adam as ONE kernel
+        (vaenar_adam_step_sharded) instead of NCCL all-reduce + Adam.  One process per GPU on one node, world <= 8."""
+        import torch.distributed as dist
+        self._require_cuda()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world < 2 or world > 8:
+            raise VaenarError("peer optimizer needs 2..8 ranks on one node")
+        if getattr(self, "_grads", None) is None:
+            self._grads = torch.zeros_like(self._flat)
+            self._losses = torch.zeros(4, dtype=torch.float32, device=self.device)
+        def export(t):
+            # cudaIpcMemHandle_t of the cudaMalloc segment that holds t + byte offset of t inside it
+            buf = ctypes.create_string_buffer(64)
+            off = ctypes.c_int64()
+            with torch.cuda.device(self.device):
+                check(self._lib.vaenar_ipc_export(self._p(t), ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(off)))
+            return bytes(buf.raw), int(off.value)
+        mine = [export(self._flat), export(self._grads)]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine, group=group)
+        self._peer_bases = []                        # IPC mappings opened on OUR device (closed in __del__)
+        pp, pg = [], []
+        with torch.cuda.device(self.device):
+            for r in range(world):
+                if r == rank:
+                    pp.append(self._flat.data_ptr())
+                    pg.append(self._grads.data_ptr())
+                    continue
+                ptrs = []
+                for handle, off in gathered[r]:
+                    base = ctypes.c_void_p()
+                    buf = ctypes.create_string_buffer(handle, 64)
+                    check(self._lib.vaenar_ipc_open(ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(base)))
+                    self._peer_bases.append(base.value)
+                    ptrs.append(base.value + off)
+                pp.append(ptrs[0])
+                pg.append(ptrs[1])
+        self._peer_params = (ctypes.c_void_p * world)(*pp)
+        self._peer_grads = (ctypes.c_void_p * world)(*pg)
+        S = int(self._lib.vaenar_adam_shard_floats(self._flat.numel(), world))
+        self._shard_m = torch.zeros(S, dtype=torch.float32, device=self.device)
+        self._shard_v = torch.zeros(S, dtype=torch.float32, device=self.device)
+        host = torch.zeros(self._flat.numel(), dtype=torch.uint8)
+        check(self._lib.vaenar_trainable_mask(self._h, ctypes.c_void_p(host.data_ptr())))
+        self._trainable_mask = host.to(self.device)
+        self._peer = (rank, world, group)
+        self._barrier_flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        dist.barrier(group=group)
+
+    def _peer_adam(self, step, grad_scale, lr=None, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        import torch.distributed as dist
+        rank, world, group = self._peer
+        lr = float(self.hps.Train.learning_rate if lr is None else lr)
+        dist.all_reduce(self._barrier_flag, group=group)          # stream-ordered barrier: every rank's gradients are final
+        check(self._lib.vaenar_adam_step_sharded(
+            ctypes.cast(self._peer_params, ctypes.c_void_p), ctypes.cast(self._peer_grads, ctypes.c_void_p),
+            self._p(self._shard_m), self._p(self._shard_v), self._p(self._trainable_mask), self._flat.numel(), rank, world,
+            int(step), lr, float(beta_1), float(beta_2), float(epsilon), float(grad_scale), self._stream()))
+        dist.all_reduce(self._barrier_flag, group=group)          # every peer has written its shard into our parameters
+        self._dirty = True
+
     def train_step(self, texts, mels, t_lengths, m_lengths, kl_weight, reduction_factor, eps=None, dropout_masks=None,
                    loss_scale=None, group=None):
         """The train_step closure of train.py:120-138: loss, gradients, (data-parallel: ONE all-reduce of the flat
@@ -530,10 +599,14 @@ class VAENAR:
         losses, grads = self.train_step_grads(texts, mels, t_lengths, m_lengths, kl_weight, reduction_factor, eps=eps,
                                               dropout_masks=dropout_masks, loss_scale=loss_scale)
         world = 1
+        self._opt_step = getattr(self, "_opt_step", 0) + 1
+        if getattr(self, "_peer", None) is not None:
+            # gradient exchange + Adam fused over NVLink peer memory (reduce-scatter -> Adam -> all-gather in one kernel)
+            self._peer_adam(self._opt_step, 1.0 / (self._last_loss_scale * self._peer[1]))
+            return losses[0], losses[1], losses[2], losses[3]
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             world = dist.get_world_size(group)
             dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=group)      # the single collective of the training path
-        self._opt_step = getattr(self, "_opt_step", 0) + 1
         self.apply_gradients(grads, self._opt_step, grad_scale=1.0 / (self._last_loss_scale * world))
         return losses[0], losses[1], losses[2], losses[3]
 
