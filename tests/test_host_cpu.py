@@ -89,3 +89,22 @@ def test_workspace_query_and_unsupported_hparams(built):
             latent_dim = 64
     with pytest.raises(VaenarError):
         VAENAR(Bad, device="cpu")
+
+
+def test_training_host_logic_without_gpu(built):
+    """train_step must fail loudly without a GPU; the training workspace query (a dry run of the whole forward + backward
+    launch sequence) and the optimiser sharding arithmetic are pure host code."""
+    from vaenar_tts_b200 import VAENAR, LJHPS, VaenarError, _lib
+    lib = _lib.load()
+    m = VAENAR(LJHPS, device="cpu")
+    small = int(lib.vaenar_train_workspace_bytes(m._h, 4, 64, 128, 2))
+    big = int(lib.vaenar_train_workspace_bytes(m._h, 32, 148, 435, 2))
+    assert 0 < small < big and 4e9 < big < 8e9, (small, big)          # C3: every saved activation, ~5.5 GB
+    assert big > 10 * int(lib.vaenar_workspace_bytes(m._h, 32, 148, 435, 2))   # inference reuses its buffers
+    n = m.flat_parameters().numel()
+    for world in (1, 2, 3, 8):
+        S = int(lib.vaenar_adam_shard_floats(n, world))
+        assert S % 4 == 0 and S * world >= n and S * (world - 1) < n + 4 * world
+    if not torch.cuda.is_available():
+        with pytest.raises(VaenarError):
+            m.train_step(torch.zeros(2, 4, dtype=torch.int32), torch.zeros(2, 8, 80), [4, 4], [8, 8], 1e-5, 2)
