@@ -643,6 +643,8 @@ static void set_attrs(vaenar_model* m) {
 #undef VB_SET_ATTR
   VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+  VB_CUDA(cudaFuncSetAttribute(attention2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
+  VB_CUDA(cudaFuncSetAttribute(attention2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_DKDV_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_DQ_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB2_DKDV_SMEM));
@@ -891,16 +893,25 @@ static void run_attention(Ctx& c, int B, int H, const AttnCall& a) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(ATT_THREADS);
-  cfg.dynamicSmemBytes = ATT_SMEM;
+  // Two variants: 128-key blocks / one CTA per SM (lowest latency when the grid fits the chip in one wave: the inference
+  // chains), 64-key blocks / two CTAs per SM (more overlap when the grid is several waves deep: the B32 training step).
+  // Measured: C2 inference 1.995 ms (v1) vs 2.022 ms (v2); C3 train step 14.30 ms (v1) vs 14.14 ms (v2).
+  static const char* att_env = getenv("VAENAR_ATTN");
+  const bool att_v1 = att_env ? att_env[0] == '1' : (grid.x * grid.y * grid.z <= 2u * 148u);
+  cfg.blockDim = dim3(att_v1 ? ATT_THREADS : ATT2_THREADS);
+  cfg.dynamicSmemBytes = att_v1 ? ATT_SMEM : ATT2_SMEM;
   cfg.stream = c.stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t le = a.ali ? cudaLaunchKernelEx(&cfg, attention_tc_kernel<true>, tQ, tK, tV, p)
-                               : cudaLaunchKernelEx(&cfg, attention_tc_kernel<false>, tQ, tK, tV, p);
+  const CUtensorMap tK64 = make_tmap(a.k, 3, a.k_ld, a.Tk, B, a.k_ld, static_cast<uint64_t>(a.Tk) * a.k_ld, 64, 64);
+  const cudaError_t le =
+      att_v1 ? (a.ali ? cudaLaunchKernelEx(&cfg, attention_tc_kernel<true>, tQ, tK, tV, p)
+                      : cudaLaunchKernelEx(&cfg, attention_tc_kernel<false>, tQ, tK, tV, p))
+             : (a.ali ? cudaLaunchKernelEx(&cfg, attention2_tc_kernel<true>, tQ, tK64, tV, p)
+                      : cudaLaunchKernelEx(&cfg, attention2_tc_kernel<false>, tQ, tK64, tV, p));
   if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(attention_tc_kernel) failed: %s", cudaGetErrorString(le));
   check_launch("attention_tc_kernel");
 }
