@@ -370,8 +370,12 @@ def run_train(args):
     frames_total = world * B * Tm * args.steps
     if rank == 0:
         pk = peaks()
+        # per-class timing pass: local (no collective on this rank alone) and with the weight-gradient stream folded into
+        # the main stream, so that every class is timed as its own execution time, not as an overlapped interval
+        os.environ["VAENAR_NO_WGRAD_STREAM"] = "1"
         lib.vaenar_profile_enable(1)
-        model.train_step_grads(d_texts, d_mels, d_t, d_m, klw, rf)      # local pass: no collective on this rank alone
+        model.train_step_grads(d_texts, d_mels, d_t, d_m, klw, rf)
+        os.environ.pop("VAENAR_NO_WGRAD_STREAM", None)
         rep = json.loads(lib.vaenar_profile_report().decode())
         lib.vaenar_profile_enable(0)
         tot_ms = sum(v["ms"] for v in rep.values()) or 1.0

@@ -250,10 +250,7 @@ static void plan_bw(vaenar_model& m, const std::string& pk, const std::string& p
   m.add_op(pk, 0, 0, param, 0, in, out, out, 2);
 }
 static void plan_bw_xblk(vaenar_model& m, const std::string& pk, const std::string& n, int d, int ffn) {
-  m.add_mat("bw." + pk + ".qkv", d, 3 * d);
   int i = 0;
-  for (const char* q : {"query", "key", "value"})
-    m.add_op("bw." + pk + ".qkv", 0, (i++) * d, n + ".self_attention." + q + "_layer.kernel", 0, d, d, d, 2);
   plan_bw(m, "bw." + pk + ".proj1", n + ".att_proj1.kernel", 2 * d, d);
   plan_bw(m, "bw." + pk + ".proj2", n + ".att_proj2.kernel", 2 * d, d);
   // K-concatenated operands: all gradient contributions to one residual-stream tensor in ONE GEMM
@@ -451,10 +448,7 @@ static void build_model(vaenar_model& m) {
     for (int i = 0; i < h.enc_n_blk; ++i) {
       const std::string n = "text_encoder.self_attentions." + std::to_string(i), pk = "bw.enc.blk" + std::to_string(i);
       const int A = h.enc_att_dim;
-      m.add_mat(pk + ".qkv", E, 3 * A);
       int c = 0;
-      for (const char* q : {"query", "key", "value"})
-        m.add_op(pk + ".qkv", 0, (c++) * A, n + ".attention." + q + "_layer.kernel", 0, E, A, A, 2);
       plan_bw(m, pk + ".proj", n + ".att_proj.kernel", E + A, E);
       m.add_mat(pk + ".xq", E, E + 3 * A);
       m.add_op(pk + ".xq", 0, 0, n + ".att_proj.kernel", 0, E, E, E, 2);
@@ -1550,10 +1544,12 @@ static void decoder_fwd(Ctx& c, const float* z, const float* text_embd, const in
   // PostNet (modules/utils.py:98-115): conv -> tanh (last: identity) -> BN; split-fp16 operands
   __half *in_h = ini_h, *in_l = ini_l, *out_h = pa_h, *out_l = pa_l;
   int cin = O;
+  static const int post_bn_env = getenv("VAENAR_POST_BN") ? atoi(getenv("VAENAR_POST_BN")) : 0;
+  const int post_bn = post_bn_env ? post_bn_env : 256;
   for (int i = 0; i < h.post_n_conv; ++i) {
     const std::string pk = "dec.post" + std::to_string(i), pn = "decoder.postnet.conv_stack." + std::to_string(i);
     conv_bn(c, pk, pn, AOp{in_h, cin, cin}, AOp{in_l, cin, cin}, B, Tm, cin, C, h.post_kernel,
-            (i < h.post_n_conv - 1) ? 2 : 0, true, 256, h.post_drop_rate, out_h, out_l);   // 256: one wave of 112 CTAs
+            (i < h.post_n_conv - 1) ? 2 : 0, true, post_bn, h.post_drop_rate, out_h, out_l);
     in_h = out_h; in_l = out_l;
     out_h = (in_h == pa_h) ? pb_h : pa_h;
     out_l = (in_l == pa_l) ? pb_l : pa_l;
