@@ -72,6 +72,11 @@ int64_t vaenar_workspace_bytes(vaenar_handle_t h, int B, int T_text, int T_z, in
  * folded inference BatchNorm, ActNorm(+)InvertibleLinear folded 128x128 maps, float64 log|det W| and the
  * fp32 inverse of modules/flow.py:126-144).  Call after every change of the parameters. */
 int vaenar_pack_weights(vaenar_handle_t h, const float* params, void* packed, void* stream);
+/* Same, but the flow constants (128x128 LU / inverse, latency-bound single-CTA kernels) keep running on an internal
+ * stream when the call returns; the NEXT call of this library with the same handle orders them before its own work
+ * (vaenar_train_step_grads does so right before the prior, so that they overlap the encoder / posterior / decoder
+ * forward).  Do not use before replaying a captured CUDA graph: the replay does not pass through the library. */
+int vaenar_pack_weights_async(vaenar_handle_t h, const float* params, void* packed, void* stream);
 
 /* TransformerEncoder.call (modules/encoder.py:79-93), training=False: text_embd [B, T_text, embd]. */
 int vaenar_text_encoder_fwd(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,

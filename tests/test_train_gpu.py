@@ -273,3 +273,31 @@ def test_full_size_c3_properties():
         assert na > 0, n
         if numel > 1:
             assert float((a - b).norm()) / na < 2e-2, (n, float((a - b).norm()) / na)
+
+
+def test_captured_session_follows_training():
+    """A CUDA-graph InferenceSession captured BEFORE training must serve the trained weights afterwards: the graph reads the
+    packed operand arena in place, the session re-packs it when the parameters changed."""
+    from vaenar_tts_b200 import InferenceSession
+    case = list(CASES)[0]
+    ohps, g, P = load_case(case)
+    m = make_model(ohps, P)
+    texts, mels, t_len, m_len = t(g, "texts"), t(g, "mels"), t(g, "t_len"), t(g, "m_len")
+    rf = 2
+    Tz = int(((m_len + rf - 1) // rf).max())
+    sess = InferenceSession(m, texts.shape[0], texts.shape[1], Tz, rf=rf)
+    sess.set_inputs(texts, t_len, m_len)
+    sess.run_e2e()
+    torch.cuda.synchronize()
+    sess.capture()
+    sess.run_e2e(new_noise=False)
+    torch.cuda.synchronize()                       # the D2H into the pinned buffer is asynchronous
+    before = sess.h_mel.clone()
+    for _ in range(3):
+        m.train_step(texts, mels, t_len, m_len, 1e-5, int(g["rf"]))
+    sess.run_e2e(new_noise=False)
+    torch.cuda.synchronize()
+    after = sess.h_mel.clone()
+    eager, _ = m.inference(texts, m_len, t_len, reduction_factor=rf, epsilon=sess.eps, return_alignments=False)
+    assert float((after - before).abs().max()) > 1e-4                      # the weights moved
+    assert float((after - eager.cpu()).abs().max()) < 1e-5                  # and the graph serves the new ones

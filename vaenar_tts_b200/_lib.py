@@ -44,6 +44,7 @@ _SIGS = {
     "vaenar_packed_bytes": (c_int64, [_P]),
     "vaenar_workspace_bytes": (c_int64, [_P, c_int, c_int, c_int, c_int]),
     "vaenar_pack_weights": (c_int, [_P, _P, _P, _P]),
+    "vaenar_pack_weights_async": (c_int, [_P, _P, _P, _P]),
     "vaenar_text_encoder_fwd": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, c_int, c_int, c_float, _P, _P]),
     "vaenar_length_predictor_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P]),
     "vaenar_prior_sample": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),

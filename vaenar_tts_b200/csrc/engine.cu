@@ -1872,6 +1872,13 @@ int vaenar_pack_weights(vaenar_handle_t h, const float* params, void* packed, vo
   API_BEGIN
   Ctx c = make_ctx(h, params, packed, nullptr, 0, stream);
   pack_weights(h, params, static_cast<uint8_t*>(packed), c.stream);
+  join_flow(c);   // everything, incl. the flow constants prepared on the internal stream, is ordered on `stream`
+  API_END
+}
+int vaenar_pack_weights_async(vaenar_handle_t h, const float* params, void* packed, void* stream) {
+  API_BEGIN
+  Ctx c = make_ctx(h, params, packed, nullptr, 0, stream);
+  pack_weights(h, params, static_cast<uint8_t*>(packed), c.stream);   // flow constants joined by the next library call
   API_END
 }
 

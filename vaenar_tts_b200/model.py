@@ -232,13 +232,14 @@ class VAENAR:
     def _f32(self, t):
         return torch.as_tensor(t).to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
 
-    def _prepare(self, B, Tt, Tz, rf):
+    def _prepare(self, B, Tt, Tz, rf, defer_flow_join=False):
         self._require_cuda()
         if self._packed is None:
             self._packed = torch.empty(int(self._lib.vaenar_packed_bytes(self._h)), dtype=torch.uint8,
                                        device=self.device)
         if self._dirty:
-            check(self._lib.vaenar_pack_weights(self._h, self._p(self._flat), self._p(self._packed), self._stream()))
+            pack = self._lib.vaenar_pack_weights_async if defer_flow_join else self._lib.vaenar_pack_weights
+            check(pack(self._h, self._p(self._flat), self._p(self._packed), self._stream()))
             self._dirty = False
         need = int(self._lib.vaenar_workspace_bytes(self._h, B, Tt, Tz, rf))
         if need < 0:
@@ -504,7 +505,7 @@ class VAENAR:
         m_len = self._i32(m_lengths)
         t_len = self._i32(t_lengths)
         z_len = (m_len + (rf - 1)) // rf
-        self._prepare(B, Tt, Tz, rf)
+        self._prepare(B, Tt, Tz, rf, defer_flow_join=True)      # joined inside vaenar_train_step_grads, before the prior
         need = int(self._lib.vaenar_train_workspace_bytes(self._h, B, Tt, Tz, rf))
         if need < 0:
             check(-1)
@@ -697,6 +698,8 @@ class InferenceSession:
             self.calls += 1
             check(self.m._lib.vaenar_randn(self.m._p(self.eps), self.eps.numel(), self.seed, self.calls, 1.0,
                                            self.m._stream()))
+        if self.m._dirty:       # weights changed since the last pack (training, load_state_dict): the graph reads the same
+            self.m._prepare(self.B, self.Tt, self.Tz, self.rf)          # arena, so re-packing in place is enough
         if self.graph is not None:
             self.graph.replay()
         else:
