@@ -254,7 +254,65 @@ class Layer:
             _state.training_stack.pop()
 
 
+def _trainable_variables(self):
+    """tf.keras.Model.trainable_variables: every variable except the BatchNorm moving statistics, in attribute order."""
+    return [v for k, v in extract_variables(self).items() if not (k.endswith("moving_mean") or k.endswith("moving_variance"))]
+
+
+Layer.trainable_variables = property(_trainable_variables)
 Model = Layer
+
+
+def enable_grad(model):
+    """Mark the trainable variables of a shim-backed model as autograd leaves (needed by GradientTape)."""
+    for v in model.trainable_variables:
+        v.requires_grad_(True)
+
+
+class GradientTape:
+    """tf.GradientTape over torch autograd: the forward pass inside the ``with`` block builds the graph as usual."""
+
+    def __init__(self, *a, **kw):
+        pass
+
+    def __enter__(self):
+        self._prev = torch.is_grad_enabled()
+        torch.set_grad_enabled(True)
+        return self
+
+    def __exit__(self, *exc):
+        torch.set_grad_enabled(self._prev)
+        return False
+
+    def gradient(self, target, sources):
+        sources = list(sources)
+        with torch.enable_grad():
+            grads = torch.autograd.grad(target, sources, allow_unused=True)
+        return [g for g in grads]
+
+
+class Adam:
+    """tf.keras.optimizers.Adam of TF 2.2 (ResourceApplyAdam): lr_t = lr sqrt(1 - b2^t) / (1 - b1^t),
+    m <- b1 m + (1-b1) g, v <- b2 v + (1-b2) g^2, var <- var - lr_t m / (sqrt(v) + eps); variables with a None gradient
+    are skipped."""
+
+    def __init__(self, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, **kw):
+        self.lr, self.b1, self.b2, self.eps = float(learning_rate), beta_1, beta_2, epsilon
+        self.iterations = 0
+        self.slots = {}
+
+    def apply_gradients(self, grads_and_vars):
+        self.iterations += 1
+        t = self.iterations
+        lr_t = self.lr * math.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)
+        with torch.no_grad():
+            for g, v in grads_and_vars:
+                if g is None:
+                    continue
+                m, vv = self.slots.setdefault(id(v), (torch.zeros_like(v), torch.zeros_like(v)))
+                m.mul_(self.b1).add_(g, alpha=1 - self.b1)
+                vv.mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+                v.sub_(lr_t * m / (vv.sqrt() + self.eps))
 
 
 def _glorot(shape_, fan_in, fan_out):
@@ -338,8 +396,9 @@ class BatchNormalization(Layer):
             dims = tuple(range(inputs.dim() - 1))
             mean = inputs.mean(dim=dims)
             var = ((inputs - mean) ** 2).mean(dim=dims)
-            self.moving_mean.copy_(self.moving_mean * self.momentum + mean * (1 - self.momentum))
-            self.moving_variance.copy_(self.moving_variance * self.momentum + var * (1 - self.momentum))
+            with torch.no_grad():   # the moving averages are not differentiated (non-trainable variables)
+                self.moving_mean.copy_(self.moving_mean * self.momentum + mean.detach() * (1 - self.momentum))
+                self.moving_variance.copy_(self.moving_variance * self.momentum + var.detach() * (1 - self.momentum))
         else:
             mean, var = self.moving_mean, self.moving_variance
         return (inputs - mean) * torch.rsqrt(var + self.epsilon) * self.gamma + self.beta
@@ -405,6 +464,7 @@ def _build_module():
     tf.logical_and = lambda a, b, **kw: a & b
     tf.Variable = Variable
     tf.function = lambda *a, **kw: (a[0] if a and callable(a[0]) else (lambda f: f))
+    tf.GradientTape = GradientTape
     tf.TensorSpec = lambda *a, **kw: None
 
     m = _NS("tensorflow.math")
@@ -442,6 +502,8 @@ def _build_module():
     keras.layers = layers
     keras.Model = Model
     keras.initializers = _NS("tensorflow.keras.initializers")
+    keras.optimizers = _NS("tensorflow.keras.optimizers")
+    keras.optimizers.Adam = Adam
     tf.keras = keras
     tf.losses = _NS("tensorflow.losses")
     tf.nest = _NS("tensorflow.nest")

@@ -96,3 +96,49 @@ def test_init(case):
     for k in P:
         if ".actnorm." in k:
             close(P[k], g["init_actnorm/" + k], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_train_step_gradients_and_adam(case):
+    """The oracle's train_step (loss of train.py:135, autograd, Keras Adam) against the golden vectors produced by the
+    reference's OWN train_step closure (train.py:127-138, compiled unmodified) over the shim
+    (tests/golden/make_golden_grads.py): losses, gradient norm + a random projection of every trainable tensor, the Adam
+    update of every tensor, full gradients of a few small tensors."""
+    import os
+    import zlib
+    from golden_util import GOLDEN_DIR
+    hps, g, P = load_case(case)
+    G = dict(np.load(os.path.join(GOLDEN_DIR, case.replace(".npz", "_train_step.npz")), allow_pickle=False))
+    Pg = {k: v.clone().requires_grad_(O.is_trainable(k)) for k, v in P.items()}
+    loss, l2, kl, ll = O.train_step_loss(Pg, hps, t(g, "texts"), t(g, "mels"), t(g, "t_len"), t(g, "m_len"), float(G["kl_weight"]),
+                                         int(g["rf"]), t(g, "train_eps"), masks=train_masks(hps, g), new_stats={})
+    loss.backward()
+    close(loss.detach(), G["loss"])
+    close(l2.detach(), G["mel_l2"])
+    close(kl.detach(), G["kl"], rtol=1e-4)
+    close(ll.detach(), G["length_l2"])
+    names = [str(n) for n in G["names"]]
+    assert sorted(names) == sorted(k for k in P if O.is_trainable(k)) and len(names) == 485
+    worst = 0.0
+    for i, k in enumerate(names):
+        gr = Pg[k].grad if Pg[k].grad is not None else torch.zeros_like(Pg[k])
+        d = torch.randn(gr.numel(), generator=torch.Generator().manual_seed(zlib.crc32(k.encode())), dtype=torch.float64)
+        flat = gr.double().reshape(-1)
+        ref_n, ref_p = float(G["grad_norm"][i]), float(G["grad_proj"][i])
+        scale = max(ref_n, 1e-12)
+        if ref_n < 1e-7:                      # mathematically zero gradients (conv bias straight into BatchNorm, unused
+            assert float(flat.norm()) < 1e-6, k   # out_projection columns): fp32 noise only
+            continue
+        e = max(abs(float(flat.norm()) - ref_n), abs(float(flat @ d) - ref_p)) / scale
+        worst = max(worst, e)
+        assert e < 2e-3, (k, e, ref_n)
+        # Keras Adam step (first step: m = (1-b1) g, v = (1-b2) g^2): compare the update itself
+        new, _, _ = O.adam_update(Pg[k].detach(), gr, torch.zeros_like(gr), torch.zeros_like(gr), 1, lr=hps.Train.learning_rate)
+        upd = (new - P[k]).double().reshape(-1)
+        un, up = float(G["upd_norm"][i]), float(G["upd_proj"][i])
+        assert abs(float(upd.norm()) - un) <= 2e-3 * un + 1e-9, (k, float(upd.norm()), un)
+        assert abs(float(upd @ d) - up) <= 1e-2 * un + 1e-9, (k, float(upd @ d), up)
+    for key in G:
+        if key.startswith("grad/"):
+            k = key[5:]
+            close(Pg[k].grad, G[key], rtol=2e-3, atol=2e-3 * float(np.abs(G[key]).max()) + 1e-12)
