@@ -560,12 +560,15 @@ class VAENAR:
                     pg.append(self._grads.data_ptr())
                     continue
                 ptrs = []
-                for handle, off in gathered[r]:
-                    base = ctypes.c_void_p()
-                    buf = ctypes.create_string_buffer(handle, 64)
-                    check(self._lib.vaenar_ipc_open(ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(base)))
-                    self._peer_bases.append(base.value)
-                    ptrs.append(base.value + off)
+                opened = {}                                  # both buffers may live in the same cudaMalloc segment:
+                for handle, off in gathered[r]:              # a handle can be opened only once per process
+                    if handle not in opened:
+                        base = ctypes.c_void_p()
+                        buf = ctypes.create_string_buffer(handle, 64)
+                        check(self._lib.vaenar_ipc_open(ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(base)))
+                        self._peer_bases.append(base.value)
+                        opened[handle] = base.value
+                    ptrs.append(opened[handle] + off)
                 pp.append(ptrs[0])
                 pg.append(ptrs[1])
         self._peer_params = (ctypes.c_void_p * world)(*pp)
