@@ -188,6 +188,10 @@ int vaenar_adam_step_sharded(float* const* peer_params, const float* const* peer
                              const uint8_t* trainable_mask, int64_t n, int rank, int world, int64_t step, float lr, float beta1,
                              float beta2, float eps, float grad_scale, void* stream);
 
+/* CRC32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start): the checksum of the TF tensor-bundle /
+ * TFRecord formats read by vaenar_tts_b200/tf_checkpoint.py (tf.train.Checkpoint files of train.py:246-248). */
+uint32_t vaenar_crc32c(const void* data, int64_t n, uint32_t crc);
+
 /* N(0, stddev) noise from the counter-based generator (replaces tf.random.normal at
  * modules/posterior.py:35 and modules/prior.py:35). */
 int vaenar_randn(float* out, int64_t n, uint64_t seed, uint64_t stream_id, float stddev, void* stream);

@@ -71,6 +71,7 @@ _SIGS = {
     "vaenar_adam_shard_floats": (c_int64, [c_int64, c_int]),
     "vaenar_adam_step_sharded": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int64, c_float, c_float, c_float, c_float,
                                          c_float, _P]),
+    "vaenar_crc32c": (ctypes.c_uint32, [_P, c_int64, ctypes.c_uint32]),
     "vaenar_randn": (c_int, [_P, c_int64, c_uint64, c_uint64, c_float, _P]),
     "vaenar_launch_count": (ctypes.c_long, []),
     "vaenar_profile_enable": (c_int, [c_int]),

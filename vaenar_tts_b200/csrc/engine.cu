@@ -2121,6 +2121,24 @@ int vaenar_ipc_close(void* ptr) {
 }
 int64_t vaenar_adam_shard_floats(int64_t n, int world) { return (n / 4 + world - 1) / world * 4; }
 
+// CRC32C (Castagnoli) of a host buffer -- checksums of the TF tensor-bundle / TFRecord formats (host code only).
+uint32_t vaenar_crc32c(const void* data, int64_t n, uint32_t crc) {
+  static uint32_t table[256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      table[i] = c;
+    }
+    init = true;
+  }
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = crc ^ 0xFFFFFFFFu;
+  for (int64_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
+
 int vaenar_randn(float* out, int64_t n, uint64_t seed, uint64_t stream_id, float stddev, void* stream) {
   API_BEGIN
   const int64_t thr = (n + 3) / 4;

@@ -178,6 +178,18 @@ class VAENAR:
                     v.copy_(src.reshape(v.shape))
         self._dirty = True
 
+    def load_tf_checkpoint(self, prefix, strict=True):
+        """Restore the model weights from a TF2 object-graph checkpoint written by the reference
+        (``tf.train.Checkpoint(model=...)``, train.py:246-248 / inference.py:39-41): ``prefix`` = ``.../ckpt-N``.
+        TensorFlow is not needed (vaenar_tts_b200/tf_checkpoint.py)."""
+        from . import tf_checkpoint
+        self.load_state_dict(tf_checkpoint.load_tf_checkpoint(prefix), strict=strict)
+
+    def save_tf_checkpoint(self, prefix, step=0):
+        """Write the weights under the reference's checkpoint keys (tensor-bundle format)."""
+        from . import tf_checkpoint
+        tf_checkpoint.save_tf_checkpoint(prefix, self.state_dict(), step=step)
+
     @property
     def trainable_variables(self):
         return [self._views[n] for n, _, _, tr in self._manifest if tr]
