@@ -261,7 +261,7 @@ def write_bundle(prefix, tensors):
     data = bytearray()
     items = [(b"", b"\x08\x01\x1a\x02\x08\x01")]            # num_shards = 1, endianness LITTLE (0, default), version {producer: 1}
     for key in sorted(tensors):
-        a = np.ascontiguousarray(tensors[key])
+        a = np.asarray(tensors[key], order="C")
         if a.dtype not in _DTYPE_ENUM:
             raise ValueError(f"{key}: unsupported dtype {a.dtype}")
         raw = a.astype(a.dtype.newbyteorder("<")).tobytes()
