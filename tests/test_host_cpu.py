@@ -108,3 +108,22 @@ def test_training_host_logic_without_gpu(built):
     if not torch.cuda.is_available():
         with pytest.raises(VaenarError):
             m.train_step(torch.zeros(2, 4, dtype=torch.int32), torch.zeros(2, 8, 80), [4, 4], [8, 8], 1e-5, 2)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port, on the host cores) prints ONE JSON line with
+    the contract keys, needs no GPU, and names the same metric / workload as our arm."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "mel-frames/sec" and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["config"]["workload"].startswith("C2:") and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert abs(d["value"] - d["cpu_baseline"]["value"]) < 1e-6 * d["value"]
