@@ -1,6 +1,6 @@
 """Static evidence from the built library (no GPU needed): per-kernel resource usage (cuobjdump -res-usage) and counts of the
 SASS mnemonics that prove the tcgen05 / TMEM / TMA path (UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = TMA tensor
-load, UTCBAR = tcgen05.commit, UTCATOMSWS = TMEM allocation, RED = fp32 reductions of the weight-gradient epilogue).
+load, UTCBAR = tcgen05.commit, UTCATOMSWS = TMEM allocation, REDG = fp32 reductions of the weight-gradient epilogue).
 usage: python tools/sass_summary.py [round]  ->  profiles/sass_<round>.md"""
 import collections
 import os
@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "vaenar_tts_b200", "libvaenar_sm100.so")
 ROUND = sys.argv[1] if len(sys.argv) > 1 else "r1"
-MN = ["UTCHMMA", "LDTM", "UTMALDG", "UTCBAR", "UTCATOMSWS", "RED", "ATOM", "SYNCS", "BAR.SYNC", "HMMA", "FFMA", "DFMA", "MUFU"]
+MN = ["UTCHMMA", "LDTM", "UTMALDG", "UTCBAR", "UTCATOMSWS", "REDG", "ATOMG", "SYNCS", "BAR.SYNC", "HMMA", "FFMA", "DFMA", "MUFU"]
 
 
 def demangle(names):
@@ -63,7 +63,7 @@ rows.sort(key=lambda r: (-r[4][0], -r[3]))
 with open(os.path.join(ROOT, "profiles", f"sass_{ROUND}.md"), "w") as f:
     f.write(f"# Static SASS / resource summary of libvaenar_sm100.so (sm_100a) -- {ROUND}\n\n"
             "`python tools/sass_summary.py` (cuobjdump -res-usage / -sass; no GPU).  UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, "
-            "UTMALDG = TMA tensor load, UTCBAR = tcgen05.commit -> mbarrier, UTCATOMSWS = TMEM alloc/dealloc, RED = "
+            "UTMALDG = TMA tensor load, UTCBAR = tcgen05.commit -> mbarrier, UTCATOMSWS = TMEM alloc/dealloc, REDG = "
             "red.global.add (weight-gradient epilogue / bias-gradient column sums), HMMA = legacy mma.sync (must be 0).\n\n"
             "| kernel | regs | stack | SASS instrs | " + " | ".join(MN) + " |\n|---|---|---|---|" + "---|" * len(MN) + "\n")
     for name, reg, stack, n, cs in rows:
