@@ -316,6 +316,8 @@ def run_train(args):
     d_texts, d_mels, d_t, d_m = (x.to(dev) for x in (texts, mels, t_len, m_len))
     model = VAENAR(HPS, device=dev, seed=OH.Train.random_seed)
     model.init(d_texts, d_m, d_t)                       # init_step of train.py:172-179 (data-dependent ActNorm)
+    if world > 1:
+        model.broadcast_parameters(0)                   # all replicas start from rank 0's initialisation
     peer = world > 1 and not args.nccl_allreduce
     if peer:
         model.enable_peer_optimizer()                   # gradient exchange + Adam as one kernel over NVLink peer memory

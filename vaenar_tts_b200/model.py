@@ -541,6 +541,14 @@ class VAENAR:
         self._last_loss_scale = S
         return (self._losses, self._grads, mel) if return_mel else (self._losses, self._grads)
 
+    def broadcast_parameters(self, src=0, group=None):
+        """Make every replica start from rank ``src``'s parameters (after ``init``: the data-dependent ActNorm
+        initialisation ran on that rank's batch) -- one broadcast of the flat parameter buffer."""
+        import torch.distributed as dist
+        self._require_cuda()
+        dist.broadcast(self._flat, src, group=group)
+        self._dirty = True
+
     def enable_peer_optimizer(self, group=None):
         """Data-parallel training over NVLink peer memory: share the flat parameter / gradient buffers of all ranks of
         ``group`` through CUDA IPC so that train_step can run the gradient exchange and Adam as ONE kernel
