@@ -29,7 +29,18 @@ def _worker(rank, world, port, out):
     P.allreduce_mean_(g)
     tmax = P.max_over_ranks(1.0 + rank)
     frames = P.gather_frames(int(mine[3].sum()))
-    out.put((rank, ids, [tuple(t.shape) for t in mine], float(g[0]), tmax, frames, int(m_len.sum())))
+    # replicas start from rank 0's parameters (host logic of VAENAR.broadcast_parameters, here over gloo on CPU tensors)
+    import __graft_entry__ as ge
+    ge.build()
+    from vaenar_tts_b200 import VAENAR, LJHPS as PH
+    m = VAENAR(PH, device="cpu", seed=100 + rank)
+    before = m.flat_parameters().clone()
+    m.broadcast_parameters(0)
+    ref = m.flat_parameters().clone()
+    dist.broadcast(ref, 0)
+    same_as_rank0 = bool(torch.equal(m.flat_parameters(), ref))
+    changed = bool(not torch.equal(before, m.flat_parameters()))
+    out.put((rank, ids, [tuple(t.shape) for t in mine], float(g[0]), tmax, frames, int(m_len.sum()), same_as_rank0, changed))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -53,3 +64,5 @@ def test_two_rank_sharding_and_collectives():
         assert abs(r[3] - 1.5) < 1e-6          # mean of the per-rank gradients 1 and 2
         assert r[4] == 2.0                      # max over ranks
         assert r[5] == r[6]                     # whole-job frames = sum over shards
+        assert r[7]                             # every replica holds rank 0's parameters after the broadcast
+    assert res[0][8] is False and res[1][8] is True   # rank 1 (different seed) was overwritten, rank 0 untouched

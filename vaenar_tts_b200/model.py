@@ -545,7 +545,6 @@ class VAENAR:
         """Make every replica start from rank ``src``'s parameters (after ``init``: the data-dependent ActNorm
         initialisation ran on that rank's batch) -- one broadcast of the flat parameter buffer."""
         import torch.distributed as dist
-        self._require_cuda()
         dist.broadcast(self._flat, src, group=group)
         self._dirty = True
 
