@@ -204,6 +204,8 @@ const char* vaenar_profile_report(void);
 /* Tuning aid: per-CTA phase timestamps (8 x u64, globaltimer ns) of the GEMM kernel into dev_buf; NULL disables. */
 int vaenar_debug_gemm_timestamps(void* dev_buf);
 const char* vaenar_debug_gemm_launches(void);
+/* Tuning aid: per-CTA phase timestamps (128 x u64) of consecutive fused row-kernel launches into dev_buf; NULL disables. */
+int vaenar_debug_xrow_timestamps(void* dev_buf);
 
 /* ---- block-level entry points (parity tests of single kernels against the oracle) ---- */
 /* out = act(A[M,K] W[K,N] + bias) (+residual, LayerNorm if ln != 0); A, W fp32 host-layout device buffers;
@@ -219,6 +221,16 @@ int vaenar_test_conv1d(const float* X, const float* W, const float* bias, int B,
 int vaenar_test_attention(const float* q, const float* k, const float* v, const int32_t* q_len,
                           const int32_t* k_len, int B, int H, int Tq, int Tk, int causal, float* ctx, float* ali,
                           void* ws, int64_t ws_bytes, void* stream);
+
+/* CrossAttentionBLK stack of one module (modules/attention.py:418-452) on caller-supplied activations:
+ * module 0 = decoder.attentions (modules/decoder.py:170-174), 1 = posterior.attentions (modules/posterior.py:100-106),
+ * 2 + s = prior.glow[s].affine_coupling.net.attentions (modules/transform.py:37-43).  x [B,T,256] fp32 is updated in
+ * place; text_embd [B,T_text,512] fp32 is the attention memory; alignments (nullable) [nblk,B,heads,T,T_text]. */
+int vaenar_xblk_stack_fwd(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes, int module,
+                          float* x, const float* text_embd, const int32_t* q_lengths, const int32_t* text_lengths, int B, int T,
+                          int T_text, float* alignments, void* stream);
+/* 1 (default): one fused tcgen05 row kernel per CrossAttentionBLK (csrc/xblk_fused.cuh); 0: the per-op launch chain. */
+int vaenar_set_fused(int on);
 
 /* Weight gradient of a Dense / Conv1D layer on tcgen05 with MN-major operands (csrc/wgrad_tc.cuh):
  * dW[tap][Cin (+Cin2)][Cout] = sum_{b,t} [X ; X2][b, t + tap - (taps-1)/2, :]^T dY[b, t, :]  (fp32 out, fp16 operands). */

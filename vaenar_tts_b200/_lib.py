@@ -5,7 +5,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvaenar_sm100.so")
+LIB_PATH = os.environ.get("VAENAR_LIB") or os.path.join(_HERE, "libvaenar_sm100.so")   # VAENAR_LIB: tuning builds only
 
 
 class VaenarError(RuntimeError):
@@ -85,6 +85,9 @@ _SIGS = {
     "vaenar_test_attention_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P,
                                           c_int64, _P]),
     "vaenar_test_wgrad": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
+    "vaenar_xblk_stack_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "vaenar_set_fused": (c_int, [c_int]),
+    "vaenar_debug_xrow_timestamps": (c_int, [_P]),
 }
 EXPORTS = tuple(_SIGS)
 

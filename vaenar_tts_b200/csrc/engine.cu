@@ -20,6 +20,7 @@
 #include "gemm_tc.cuh"
 #include "simt_kernels.cuh"
 #include "wgrad_tc.cuh"
+#include "xblk_fused.cuh"
 #include "bwd_kernels.cuh"
 
 using namespace vb;
@@ -574,11 +575,13 @@ struct KernelStat {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
 };
 static long g_launch_count = 0;
+static bool g_use_fused = true;   // fused per-CrossAttentionBLK row kernel (VAENAR_FUSED=0 selects the per-op launch chain)
 static bool g_use_pdl = true;   // programmatic dependent launch between the tensor-core kernels (VAENAR_NO_PDL=1 disables)
 static unsigned long long* g_dbg_cursor = nullptr;   // tuning aid: per-CTA phase timestamps of GEMM launches
 static unsigned long long* g_dbg_base = nullptr;
 static std::vector<std::string> g_dbg_launches;
 static bool g_dbg_attn = true;
+static unsigned long long* g_xrow_dbg = nullptr;   // tuning aid: per-CTA phase timestamps of the fused row kernel (128 x u64 per CTA)
 static bool g_profile = false;
 static std::map<std::string, KernelStat> g_stats;
 static std::string g_profile_json;
@@ -630,6 +633,8 @@ static void set_attrs(vaenar_model* m) {
   static bool done = false;
   if (done) return;
   if (const char* e = getenv("VAENAR_NO_PDL")) g_use_pdl = !(e[0] == '1');
+  if (const char* e = getenv("VAENAR_FUSED")) g_use_fused = !(e[0] == '0');
+  VB_CUDA(cudaFuncSetAttribute(xblk_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XR_SMEM));
 #define VB_SET_ATTR(BN, MODE, FEAT)                                                                  \
   VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, (FEAT)>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                GemmCfg<BN>::kSmemBytes));
@@ -1081,20 +1086,94 @@ static XblkBufs xblk_bufs(Ctx& c, int B, int T, int d, int H, int ffn) {
   return b;
 }
 
-// CrossAttentionBLK.call (modules/attention.py:436-452); x updated in place.
+// Fused row kernel of one CrossAttentionBLK (csrc/xblk_fused.cuh): everything after the causal self-attention core, plus
+// (next_pk non-empty) the q|k|v projections of the NEXT block, in one launch.  b.ctx holds the self-attention context.
+static bool xrow_supported(int d, int H, int ffn, int Tt, const MemKV& kv) {
+  return g_use_fused && d == XR_D && H == XR_H && ffn == XR_F && kv.d == XR_D && Tt >= 1 && Tt <= XR_TK_MAX;
+}
+static void run_xblk_row(Ctx& c, const std::string& pk, const std::string& pn, const std::string& next_pk, Stream2 x,
+                         const XblkBufs& b, int B, int T, const int* q_len, const MemKV& kv, int kv_blk, int Tt,
+                         const int* t_len, float* ali) {
+  if (c.dry) return;
+  const int d = XR_D, H = XR_H;
+  XRowParams p;
+  memset(&p, 0, sizeof(p));
+  p.T = T; p.Tt = Tt; p.TKP = cdiv(Tt, 16) * 16;
+  p.kv_col0 = kv_blk * kv.d;
+  p.vt_row0 = kv_blk * B * H * 64;
+  p.vt = kv.vt; p.vt_ld = kv.tpad;
+  p.q_len = q_len; p.k_len = t_len;
+  p.scale = 1.0f / sqrtf(64.f);   // attention.py:227-229, temperature 1.0
+  p.ln_eps = 1e-3f;               // Keras LayerNormalization default
+  p.vec[0] = c.P(pn + ".att_proj1.bias"); p.vec[1] = c.P(pn + ".layer_norm1.gamma"); p.vec[2] = c.P(pn + ".layer_norm1.beta");
+  p.vec[3] = c.P(pn + ".att_proj2.bias"); p.vec[4] = c.P(pn + ".layer_norm2.gamma"); p.vec[5] = c.P(pn + ".layer_norm2.beta");
+  p.vec[6] = c.P(pn + ".ffn.dense2.bias"); p.vec[7] = c.P(pn + ".ffn.layer_norm.gamma"); p.vec[8] = c.P(pn + ".ffn.layer_norm.beta");
+  p.bf1 = c.P(pn + ".ffn.dense1.bias");
+  p.x_f = x.f;
+  p.has_next = next_pk.empty() ? 0 : 1;
+  p.qk_next = b.qk; p.vt_next = b.vt; p.vt_next_ld = b.tpad;
+  p.ali = ali;
+  if (g_xrow_dbg) {
+    p.dbg = g_xrow_dbg;
+    g_xrow_dbg += static_cast<size_t>(cdiv(T, 128)) * B * 128;
+  }
+  const uint64_t T64 = static_cast<uint64_t>(T);
+  const CUtensorMap tX = make_tmap(x.h, 3, d, T, B, d, T64 * d, 64, 128);
+  const CUtensorMap tA1 = make_tmap(b.ctx, 3, d, T, B, d, T64 * d, 64, 128);
+  const int kld = kv.nblk * kv.d;
+  const CUtensorMap tK = make_tmap(kv.k, 3, kld, Tt, B, kld, static_cast<uint64_t>(Tt) * kld, 64, 128);
+  const CUtensorMap tV = make_tmap(kv.vt, 2, Tt, static_cast<uint64_t>(kv.nblk) * B * H * 64, 1, kv.tpad, 0, 64, 64);
+  const CUtensorMap tW1 = make_tmap(c.W(pk + ".proj1"), 2, 2 * d, d, 1, 2 * d, 0, 64, 128);
+  const CUtensorMap tWq = make_tmap(c.W(pk + ".cq"), 2, d, d, 1, d, 0, 64, 128);
+  const CUtensorMap tW2 = make_tmap(c.W(pk + ".proj2"), 2, 2 * d, d, 1, 2 * d, 0, 64, 128);
+  const CUtensorMap tF1 = make_tmap(c.W(pk + ".ffn1"), 2, d, XR_F, 1, d, 0, 64, 128);
+  const CUtensorMap tF2 = make_tmap(c.W(pk + ".ffn2"), 2, XR_F, d, 1, XR_F, 0, 64, 128);
+  const CUtensorMap tWn = p.has_next ? make_tmap(c.W(next_pk + ".qkv"), 2, d, 3 * d, 1, d, 0, 64, 128) : tWq;
+  const double rows = static_cast<double>(B) * T;
+  const double macs_row = 2.0 * d * d + d * d + 2.0 * Tt * d + 2.0 * d * d + 2.0 * d * XR_F + (p.has_next ? 3.0 * d * d : 0.0);
+  const double wbytes = 2.0 * (4.0 * d * d + d * d + 2.0 * d * XR_F + (p.has_next ? 3.0 * d * d : 0.0));
+  ProfileScope prof(ali ? "xblk_row_ali" : "xblk_row", 2.0 * rows * macs_row,
+                    wbytes + rows * d * (4 + 2 + 2 + 4 + 2) + (p.has_next ? rows * 3 * d * 2 : 0) +
+                        static_cast<double>(B) * Tt * 2 * d * 2 + (ali ? rows * H * Tt * 4 : 0),
+                    c.stream);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(cdiv(T, 128), B);
+  cfg.blockDim = dim3(XR_THREADS);
+  cfg.dynamicSmemBytes = XR_SMEM;
+  cfg.stream = c.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, xblk_row_kernel, tX, tA1, tK, tV, tW1, tWq, tW2, tF1, tF2, tWn, p);
+  if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(xblk_row_kernel) failed: %s", cudaGetErrorString(le));
+  check_launch("xblk_row_kernel");
+}
+
+// CrossAttentionBLK.call (modules/attention.py:436-452); x updated in place.  `qkv_ready` (in/out): the self-attention
+// q|k|v of THIS block already sit in b.qk / b.vt (written by the previous block's fused row kernel); on return it tells
+// the same about the block named by next_pk.
 static void xblk_fwd(Ctx& c, const std::string& pk, const std::string& pn, Stream2 x, const XblkBufs& b, int B, int T,
                      int d, int H, int ffn, const int* q_len, const MemKV& kv, int kv_blk, int Tt, const int* t_len,
-                     float* ali) {
+                     float* ali, const std::string& next_pk, bool& qkv_ready) {
   const int rows = B * T;
-  {  // self-attention projections: Q | K row-major, V transposed
+  if (!qkv_ready) {  // self-attention projections: Q | K row-major, V transposed
     GemmParams p = gp();
     p.mode = EPI_QKV; p.N = 3 * d; segs_plain(p, d);
     p.seq_T = T; p.seq_B = B; p.n_rowmajor = 2 * d; p.out_h = b.qk; p.ld_h = 2 * d;
     p.vt = b.vt; p.vt_ld = b.tpad; p.heads = H;
     run_gemm(c, 256, AOp{x.h, d, d}, AOp{}, 1, rows, c.W(pk + ".qkv"), d, 3 * d, p);
   }
+  qkv_ready = false;
   run_attention(c, B, H, AttnCall{b.qk, 2 * d, 0, T, b.qk, 2 * d, d, T, b.vt, static_cast<long>(B) * H * 64, b.tpad, 0,
                                   q_len, q_len, 1, b.ctx, d, nullptr});
+  if (xrow_supported(d, H, ffn, Tt, kv)) {
+    run_xblk_row(c, pk, pn, next_pk, x, b, B, T, q_len, kv, kv_blk, Tt, t_len, ali);
+    qkv_ready = !next_pk.empty();
+    return;
+  }
   {  // LN1(att_proj1([x ; a1]) + x)
     GemmParams p = gp();
     p.mode = EPI_LN; p.N = d; segs_concat(p, d, d);
@@ -1134,6 +1213,16 @@ static void xblk_fwd(Ctx& c, const std::string& pk, const std::string& pn, Strea
     p.out_f32 = x.f; p.ld_f32 = d; p.out_h = x.h; p.ld_h = d;
     run_gemm(c, d / 2, AOp{b.hid, ffn, ffn}, AOp{}, 1, rows, c.W(pk + ".ffn2"), ffn, d, p);
   }
+}
+// all blocks of one module in sequence (the fused row kernel of block i also projects q|k|v of block i+1)
+static void xblk_stack_fwd(Ctx& c, const std::string& pk_prefix, const std::string& pn_prefix, int nblk, Stream2 x,
+                           const XblkBufs& b, int B, int T, int d, int H, int ffn, const int* q_len, const MemKV& kv,
+                           int kv_blk0, int Tt, const int* t_len, float* ali, int64_t ali_blk_stride) {
+  bool qkv_ready = false;
+  for (int i = 0; i < nblk; ++i)
+    xblk_fwd(c, pk_prefix + std::to_string(i), pn_prefix + std::to_string(i), x, b, B, T, d, H, ffn, q_len, kv, kv_blk0 + i,
+             Tt, t_len, ali ? ali + static_cast<int64_t>(i) * ali_blk_stride : nullptr,
+             i + 1 < nblk ? pk_prefix + std::to_string(i + 1) : std::string(), qkv_ready);
 }
 
 // Conv1D wrapper of the reference: conv -> activation -> BatchNorm -> dropout (modules/utils.py:56-85).
@@ -1282,9 +1371,8 @@ static void coupling_step(Ctx& c, int s, bool backward, float* z, __half* zh, fl
     p.out_f32 = x.f; p.ld_f32 = d; p.out_h = x.h; p.ld_h = d;
     run_gemm(c, 128, AOp{c.dry ? nullptr : zh + cond_off, L, L / 2}, AOp{}, 1, rows, c.W(pk + ".pre"), kpad64(L / 2), d, p);
   }
-  for (int j = 0; j < h.prior_n_tblk; ++j)
-    xblk_fwd(c, pk + ".blk" + std::to_string(j), pn + ".attentions." + std::to_string(j), x, xb, B, Tz, d, H, F, z_len, kv,
-             s * h.prior_n_tblk + j, Tt, t_len, nullptr);
+  xblk_stack_fwd(c, pk + ".blk", pn + ".attentions.", h.prior_n_tblk, x, xb, B, Tz, d, H, F, z_len, kv, s * h.prior_n_tblk, Tt,
+                 t_len, nullptr, 0);
   {
     GemmParams p = gp();
     p.mode = EPI_COUPLING; p.N = L; segs_plain(p, d);
@@ -1483,9 +1571,8 @@ static void posterior_fwd(Ctx& c, const float* mels, const float* text_embd, con
       }
     }
   }
-  for (int i = 0; i < h.posterior_nblk; ++i)
-    xblk_fwd(c, "post.blk" + std::to_string(i), "posterior.attentions." + std::to_string(i), x, xb, B, Tz, d, H, F, z_len, kv,
-             i, Tt, t_len, nullptr);
+  xblk_stack_fwd(c, "post.blk", "posterior.attentions.", h.posterior_nblk, x, xb, B, Tz, d, H, F, z_len, kv, 0, Tt, t_len,
+                 nullptr, 0);
   {
     GemmParams p = gp();
     p.mode = EPI_POSTERIOR; p.N = 2 * L; segs_plain(p, d);
@@ -1531,9 +1618,8 @@ static void decoder_fwd(Ctx& c, const float* z, const float* text_embd, const in
     p.out_f32 = x.f; p.ld_f32 = d; p.out_h = x.h; p.ld_h = d;
     run_gemm(c, 128, AOp{zh, L, L}, AOp{}, 1, static_cast<int>(rows), c.W("dec.pre"), L, d, p);
   }
-  for (int i = 0; i < h.dec_nblk; ++i)
-    xblk_fwd(c, "dec.blk" + std::to_string(i), "decoder.attentions." + std::to_string(i), x, xb, B, Tz, d, H, F, z_len, kv, i,
-             Tt, t_len, ali ? ali + static_cast<int64_t>(i) * (ali_blk_stride ? ali_blk_stride : static_cast<int64_t>(B) * H * Tz * Tt) : nullptr);
+  xblk_stack_fwd(c, "dec.blk", "decoder.attentions.", h.dec_nblk, x, xb, B, Tz, d, H, F, z_len, kv, 0, Tt, t_len, ali,
+                 ali_blk_stride ? ali_blk_stride : static_cast<int64_t>(B) * H * Tz * Tt);
   {  // out_projection, first rf*80 columns only (decoder.py:193); [B*Tz, rf*80] == [B*Tz*rf, 80]
     GemmParams p = gp();
     p.mode = EPI_PLAIN; p.N = rf * O; segs_plain(p, d);
@@ -1630,7 +1716,8 @@ static void inference_one(Ctx& c, const int* texts, const int* t_len, const int*
 static void inference_fwd(Ctx& c, const int* texts, const int* t_len, const int* z_len, int B, int Tt, int Tz, int rf,
                           float* z_io, float* text_embd, float* mel, float* ali, float* logp) {
   const vaenar_hparams_t& h = c.m->hp;
-  const int B0 = B >= 4 ? B / 2 : B, B1 = B - B0;
+  static const bool single_chain = getenv("VAENAR_SINGLE_CHAIN") != nullptr;   // A/B timing aid
+  const int B0 = (B >= 4 && !single_chain) ? B / 2 : B, B1 = B - B0;
   const int64_t ali_stride = static_cast<int64_t>(B) * h.dec_heads * Tz * Tt;
   const int64_t mark = c.ws_off;
   if (B1 == 0) {
@@ -2156,6 +2243,11 @@ int vaenar_debug_gemm_timestamps(void* dev_buf) {
   g_dbg_launches.clear();
   return 0;
 }
+// Fused row kernel: consecutive launches write 128 x u64 per CTA (grid order) into dev_buf; null disables.
+int vaenar_debug_xrow_timestamps(void* dev_buf) {
+  g_xrow_dbg = static_cast<unsigned long long*>(dev_buf);
+  return 0;
+}
 // JSON list of the GEMM launches recorded since the buffer was set: [{"grid": [x, y], "cls": ..., "offset": u64 index}]
 const char* vaenar_debug_gemm_launches(void) {
   static std::string out;
@@ -2320,6 +2412,51 @@ int vaenar_test_attention(const float* q, const float* k, const float* v, const 
   const long nc = static_cast<long>(B) * Tq * D;
   half_to_float_kernel<<<static_cast<unsigned>((nc + 255) / 256), 256, 0, c.stream>>>(ch, ctx, nc);
   check_launch("half_to_float");
+  API_END
+}
+
+// Selects the fused per-block row kernel (1, default) or the per-op launch chain (0) for every later forward call.
+int vaenar_set_fused(int on) {
+  set_attrs(nullptr);
+  g_use_fused = on != 0;
+  return 0;
+}
+
+/* The CrossAttentionBLK stack of one module on caller-supplied activations (block-level parity hook):
+ * module 0 = decoder.attentions, 1 = posterior.attentions, 2 + s = prior.glow.s.affine_coupling.net.attentions. */
+int vaenar_xblk_stack_fwd(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes, int module,
+                          float* x, const float* text_embd, const int32_t* q_lengths, const int32_t* text_lengths, int B, int T,
+                          int T_text, float* alignments, void* stream) {
+  API_BEGIN
+  Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
+  const vaenar_hparams_t& hp = h->hp;
+  const int E = hp.enc_hidden;
+  std::string pk, pn, kvname;
+  int nblk, d, H, F, kv_nblk, kv_blk0 = 0;
+  if (module == 0) {
+    pk = "dec.blk"; pn = "decoder.attentions."; kvname = "dec.kv";
+    nblk = kv_nblk = hp.dec_nblk; d = hp.dec_att_dim; H = hp.dec_heads; F = hp.dec_ffn;
+  } else if (module == 1) {
+    pk = "post.blk"; pn = "posterior.attentions."; kvname = "post.kv";
+    nblk = kv_nblk = hp.posterior_nblk; d = hp.posterior_att_dim; H = hp.posterior_heads; F = hp.posterior_ffn;
+  } else if (module >= 2 && module < 2 + hp.prior_n_blk) {
+    const int s = module - 2;
+    pk = "prior." + std::to_string(s) + ".blk"; pn = "prior.glow." + std::to_string(s) + ".affine_coupling.net.attentions.";
+    kvname = "prior.kv";
+    nblk = hp.prior_n_tblk; kv_nblk = hp.prior_n_blk * hp.prior_n_tblk; kv_blk0 = s * hp.prior_n_tblk;
+    d = hp.prior_att_dim; H = hp.prior_heads; F = hp.prior_ffn;
+  } else {
+    VB_THROW("unknown module %d", module);
+  }
+  const int64_t rows = static_cast<int64_t>(B) * T;
+  __half* emb_h = c.alloc<__half>(static_cast<int64_t>(B) * T_text * E);
+  run_cast(c, text_embd, emb_h, static_cast<int64_t>(B) * T_text * E);
+  Stream2 xs{x, c.alloc<__half>(rows * d)};
+  run_cast(c, x, xs.h, rows * d);
+  XblkBufs xb = xblk_bufs(c, B, T, d, H, F);
+  MemKV kv = memory_kv(c, kvname, emb_h, B, T_text, E, kv_nblk, d, H);
+  xblk_stack_fwd(c, pk, pn, nblk, xs, xb, B, T, d, H, F, q_lengths, kv, kv_blk0, T_text, text_lengths, alignments,
+                 static_cast<int64_t>(B) * H * T * T_text);
   API_END
 }
 

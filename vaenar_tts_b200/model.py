@@ -405,6 +405,28 @@ class VAENAR:
                                            self._stream()))
         return initial, mel, self._ali_dict(ali)
 
+    def cross_attention_blocks(self, module, x, memory, query_lengths, memory_lengths, return_alignments=False):
+        """The CrossAttentionBLK stack (modules/attention.py:418-452) of one sub-module on caller-supplied activations:
+        ``module`` = "decoder" (modules/decoder.py:170-174), "posterior" (modules/posterior.py:100-106) or ("prior", s)
+        for the coupling net of flow step s (modules/transform.py:37-43).  Block-level parity hook of the C ABI."""
+        if module == "decoder":
+            mid, nb = 0, self._hp.dec_nblk
+        elif module == "posterior":
+            mid, nb = 1, self._hp.posterior_nblk
+        else:
+            mid, nb = 2 + int(module[1]), self._hp.prior_n_tblk
+        x = self._f32(x).clone()
+        mem = self._f32(memory)
+        B, T, _ = x.shape
+        Tt = mem.shape[1]
+        q_len, t_len = self._i32(query_lengths), self._i32(memory_lengths)
+        self._prepare(B, Tt, T, 1)
+        ali = torch.empty(nb, B, 4, T, Tt, dtype=torch.float32, device=self.device) if return_alignments else None
+        check(self._lib.vaenar_xblk_stack_fwd(self._h, self._p(self._flat), self._p(self._packed), self._p(self._ws),
+                                              self._ws.numel(), mid, self._p(x), self._p(mem), self._p(q_len),
+                                              self._p(t_len), B, T, Tt, self._p(ali), self._stream()))
+        return x, ali
+
     def _ali_dict(self, ali):
         if ali is None:
             return {}
