@@ -168,8 +168,14 @@ int vaenar_train_step_grads(vaenar_handle_t h, float* params, const void* packed
  * statistics and padding; grad_scale folds the 1/world_size of the data-parallel gradient mean.  The gradients
  * come from vaenar_train_step_grads. */
 int vaenar_trainable_mask(vaenar_handle_t h, uint8_t* host_mask);
+/* skip_flag (device, nullable): when *skip_flag != 0 the whole update is skipped (non-finite gradients, see below). */
 int vaenar_adam_step(float* params, const float* grads, float* m, float* v, const uint8_t* trainable_mask, int64_t n,
-                     int64_t step, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+                     int64_t step, float lr, float beta1, float beta2, float eps, float grad_scale, const float* skip_flag,
+                     void* stream);
+/* Overflow guard of the loss-scaled fp16 backward pass (no counterpart in the fp32 reference): adds the number of
+ * non-finite entries of grads[0, n) to *count (device float, zeroed by the caller).  Data-parallel runs all-reduce the
+ * count so that every replica skips the same step; the host backs the loss scale off (VAENAR.train_step). */
+int vaenar_grad_nonfinite(const float* grads, int64_t n, float* count, void* stream);
 
 /* Data-parallel variant (one process per GPU, world <= 8): the gradient exchange and the optimiser in ONE kernel over
  * NVLink peer memory.  peer_params / peer_grads: HOST arrays of `world` device pointers to every replica's flat parameter
@@ -186,7 +192,7 @@ int vaenar_ipc_close(void* ptr);
 int64_t vaenar_adam_shard_floats(int64_t n, int world);
 int vaenar_adam_step_sharded(float* const* peer_params, const float* const* peer_grads, float* m_shard, float* v_shard,
                              const uint8_t* trainable_mask, int64_t n, int rank, int world, int64_t step, float lr, float beta1,
-                             float beta2, float eps, float grad_scale, void* stream);
+                             float beta2, float eps, float grad_scale, const float* skip_flag, void* stream);
 
 /* CRC32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start): the checksum of the TF tensor-bundle /
  * TFRecord formats read by vaenar_tts_b200/tf_checkpoint.py (tf.train.Checkpoint files of train.py:246-248). */

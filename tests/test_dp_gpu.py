@@ -40,7 +40,8 @@ def _worker(rank, world, port, q):
     flat = m.flat_parameters().clone()
     ref = flat.clone()
     dist.broadcast(ref, 0)
-    same = float((flat - ref).abs().max())
+    mask = m._trainable_mask.bool()
+    same = float((flat - ref)[mask].abs().max())      # BatchNorm moving statistics are per-replica, everything else must agree
     q.put((rank, err, same, bool(torch.isfinite(flat).all())))
     dist.barrier()
     dist.destroy_process_group()
@@ -62,8 +63,9 @@ def test_two_gpu_train_step_allreduce():
     for rank, err, same, finite in res:
         assert err < 1e-3, (rank, err)        # atomics order only
         assert finite
-    # trainable parameters identical on both ranks after the step (BatchNorm moving statistics are per-replica)
-    assert res[1][2] < 1.0, res
+    # trainable parameters bit-identical on both ranks after the step (same all-reduced gradients, same Adam)
+    for rank, _, same, _ in res:
+        assert same == 0.0, res
 
 
 def _peer_worker(rank, world, port, q):
@@ -86,6 +88,7 @@ def _peer_worker(rank, world, port, q):
         dist.all_reduce(ref)                                              # baseline: NCCL all-reduce + fused Adam
         m1.apply_gradients(ref, step, grad_scale=1.0 / (S * world))
         m2._grads.copy_(grads)                                            # fused: peer reduce-scatter -> Adam -> all-gather
+        m2._ovf = torch.zeros(1, device="cuda")
         m2._peer_adam(step, 1.0 / (S * world))
         torch.cuda.synchronize()
         worst = max(worst, float((m1.flat_parameters() - m2.flat_parameters()).abs().max()))
@@ -124,3 +127,57 @@ def test_two_gpu_peer_memory_optimizer_matches_allreduce_adam():
         assert worst <= 1e-6, (rank, worst)       # same sums (two addends commute); Adam differs by FMA contraction (1 ulp)
         assert same == 0.0, (rank, same)          # every replica holds the same trainable parameters after the step
         assert finite
+
+
+def test_sharded_adam_single_gpu_two_local_peers():
+    """vaenar_adam_step_sharded with world = 2 where both "replicas" live on this GPU (plain device pointers instead of IPC
+    mappings): rank 0 then rank 1 each reduce their gradient shard over both gradient buffers, apply Adam with their shard
+    of the moments and write both parameter replicas.  Reference: vaenar_adam_step on the summed gradients.  Covers the
+    exchange kernel on a 1-GPU box; also the overflow skip flag."""
+    import ctypes
+    from vaenar_tts_b200 import VAENAR, LJHPS, _lib
+    from vaenar_tts_b200._lib import check
+    lib = _lib.load()
+    ref_m = VAENAR(LJHPS, device="cuda", seed=5)
+    n = ref_m.flat_parameters().numel()
+    world, S = 2, 65536.0
+    p0 = ref_m.flat_parameters().clone()
+    reps = [p0.clone(), p0.clone()]
+    shard = int(lib.vaenar_adam_shard_floats(n, world))
+    ms = [torch.zeros(shard, device="cuda") for _ in range(world)]
+    vs = [torch.zeros(shard, device="cuda") for _ in range(world)]
+    host = torch.zeros(n, dtype=torch.uint8)
+    check(lib.vaenar_trainable_mask(ref_m._h, ctypes.c_void_p(host.data_ptr())))
+    mask = host.cuda()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    flag = torch.zeros(1, device="cuda")
+    for step in (1, 2, 3):
+        gs = [(torch.randn(n, generator=torch.Generator().manual_seed(10 * step + r)) * S * 1e-3).cuda() for r in range(world)]
+        ref_m.apply_gradients(gs[0] + gs[1], step, grad_scale=1.0 / (S * world))
+        pp = (ctypes.c_void_p * world)(*[t.data_ptr() for t in reps])
+        pg = (ctypes.c_void_p * world)(*[t.data_ptr() for t in gs])
+        for r in range(world):
+            check(lib.vaenar_adam_step_sharded(ctypes.cast(pp, ctypes.c_void_p), ctypes.cast(pg, ctypes.c_void_p),
+                                               ctypes.c_void_p(ms[r].data_ptr()), ctypes.c_void_p(vs[r].data_ptr()),
+                                               ctypes.c_void_p(mask.data_ptr()), n, r, world, step, 1.25e-4, 0.9, 0.999, 1e-7,
+                                               1.0 / (S * world), ctypes.c_void_p(flag.data_ptr()), stream))
+        torch.cuda.synchronize()
+        assert torch.equal(reps[0], reps[1])                                  # all-gather: both replicas identical
+        tm = mask.bool()
+        assert float((reps[0] - ref_m.flat_parameters())[tm].abs().max()) <= 1e-6
+        assert torch.equal(reps[0][~tm], p0[~tm])                             # BatchNorm moving statistics untouched
+    # overflow: a non-finite gradient entry anywhere -> the counted flag makes every rank skip the whole update
+    before = reps[0].clone()
+    gs[1][12345] = float("inf")
+    flag.zero_()
+    for r in range(world):
+        check(lib.vaenar_grad_nonfinite(ctypes.c_void_p(gs[r].data_ptr()), n, ctypes.c_void_p(flag.data_ptr()), stream))
+    assert float(flag) == 1.0
+    pg = (ctypes.c_void_p * world)(*[t.data_ptr() for t in gs])
+    for r in range(world):
+        check(lib.vaenar_adam_step_sharded(ctypes.cast(pp, ctypes.c_void_p), ctypes.cast(pg, ctypes.c_void_p),
+                                           ctypes.c_void_p(ms[r].data_ptr()), ctypes.c_void_p(vs[r].data_ptr()),
+                                           ctypes.c_void_p(mask.data_ptr()), n, r, world, 4, 1.25e-4, 0.9, 0.999, 1e-7,
+                                           1.0 / (S * world), ctypes.c_void_p(flag.data_ptr()), stream))
+    torch.cuda.synchronize()
+    assert torch.equal(reps[0], before) and torch.equal(reps[1], before)

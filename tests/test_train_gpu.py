@@ -275,6 +275,88 @@ def test_full_size_c3_properties():
             assert float((a - b).norm()) / na < 2e-2, (n, float((a - b).norm()) / na)
 
 
+def test_full_size_c3_losses_vs_oracle():
+    """BASELINE.json configs[2] (C3: B32, T_text 148, T_mel 870) at FULL size against the oracle's training-mode forward
+    (train.py:129-135 with the same injected posterior noise and dropout masks): mel_l2, kl, length_l2 and the total at the
+    north-star tolerance 1e-3 (length loss: a square of a small log ratio, 5e-3), plus the decoded mel (MAE <= 1e-3)."""
+    from oracle.hparams import LJHPS as OLJ
+    B, Tt, Tm, rf = 32, 148, 870, 2
+    P = O.init_params(OLJ, seed=61, zero_init_std=0.02)
+    texts, mels, t_len, m_len = O.synthetic_batch(OLJ, B, Tt, Tm, rf=rf, seed=62)
+    Tz = (Tm + rf - 1) // rf
+    gen = torch.Generator().manual_seed(63)
+    eps = torch.randn(B, 1, Tz, 128, generator=gen)
+    order, masks = _random_masks(OLJ, B, Tt, Tz, rf, gen)
+    with torch.no_grad():
+        loss, l2, kl, ll = O.train_step_loss(P, OLJ, texts, mels, t_len, m_len, 1e-5, rf, eps, masks=masks, new_stats={})
+    m = make_model(OLJ, P)
+    losses, _ = m.train_step_grads(texts, mels, t_len, m_len, 1e-5, rf, eps=eps, dropout_masks=[masks[n] for n in order],
+                                   update_bn_stats=False)
+    torch.cuda.synchronize()
+    got = [float(x) for x in losses.cpu()]
+    print("C3 losses cuda", got, "oracle", [float(loss), float(l2), float(kl), float(ll)])
+    assert abs(got[0] - float(loss)) <= 1e-3 * abs(float(loss))
+    assert abs(got[1] - float(l2)) <= 1e-3 * abs(float(l2))
+    assert abs(got[2] - float(kl)) <= 1e-3 * abs(float(kl))
+    assert abs(got[3] - float(ll)) <= 5e-3 * abs(float(ll))
+
+
+def test_overflow_guard_skips_step_and_backs_off():
+    """Loss-scaled fp16 gradient operands: a step whose gradients are not finite must leave parameters and Adam moments
+    untouched and halve the dynamic loss scale; the next step (at a sane scale) trains normally."""
+    case = list(CASES)[0]
+    ohps, g, P = load_case(case)
+    m = make_model(ohps, P)
+    texts, mels, t_len, m_len = t(g, "texts"), t(g, "mels"), t(g, "t_len"), t(g, "m_len")
+    rf = int(g["rf"])
+    m.train_step(texts, mels, t_len, m_len, 1e-5, rf)          # creates the optimiser state
+    torch.cuda.synchronize()
+    assert m.skipped_steps == 0 and m.loss_scale == 65536.0
+    before = m.flat_parameters().clone()
+    mom = m._adam_m.clone()
+    m._loss_scale = 2.0 ** 40                                  # forces fp16 overflow of the gradient operands
+    m.train_step(texts, mels, t_len, m_len, 1e-5, rf)
+    torch.cuda.synchronize()
+    mask = m._trainable_mask.bool()
+    assert torch.equal(m.flat_parameters()[mask], before[mask]), "an overflowing step must not touch the parameters"
+    assert torch.equal(m._adam_m, mom)
+    assert m.skipped_steps == 1 and m.loss_scale == 2.0 ** 39
+    m._loss_scale = 65536.0
+    m.train_step(texts, mels, t_len, m_len, 1e-5, rf)
+    torch.cuda.synchronize()
+    assert m.skipped_steps == 1
+    assert not torch.equal(m.flat_parameters()[mask], before[mask])
+    assert torch.isfinite(m.flat_parameters()).all()
+
+
+def test_fp16_range_stress_fails_loudly():
+    """fp16 operands have a 65504 ceiling.  Scale the first FFN of a decoder block so that its hidden activations exceed it:
+    the forward must either stay finite or raise (check_finite) -- never return non-finite mels silently; a training step
+    on the same weights must be skipped by the overflow guard rather than poison the parameters."""
+    from vaenar_tts_b200._lib import VaenarError
+    case = list(CASES)[0]
+    ohps, g, P = load_case(case)
+    P = {k: v.clone() for k, v in P.items()}
+    P["decoder.attentions.0.ffn.dense1.kernel"] *= 3.0e4        # hidden ~ 1e5..1e6 >> 65504
+    m = make_model(ohps, P)
+    texts, mels, t_len, m_len = t(g, "texts"), t(g, "mels"), t(g, "t_len"), t(g, "m_len")
+    rf = int(g["rf"])
+    try:
+        mel, _ = m.inference(texts, m_len, t_len, reduction_factor=rf, check_finite=True)
+        torch.cuda.synchronize()
+        assert torch.isfinite(mel).all()
+    except VaenarError as e:
+        assert "non-finite" in str(e)
+    before = m.flat_parameters().clone()
+    m.train_step(texts, mels, t_len, m_len, 1e-5, rf)
+    torch.cuda.synchronize()
+    after = m.flat_parameters()
+    assert torch.isfinite(after).all(), "non-finite gradients reached the parameters"
+    if m.skipped_steps:
+        mask = m._trainable_mask.bool()
+        assert torch.equal(after[mask], before[mask])
+
+
 def test_captured_session_follows_training():
     """A CUDA-graph InferenceSession captured BEFORE training must serve the trained weights afterwards: the graph reads the
     packed operand arena in place, the session re-packs it when the parameters changed."""

@@ -13,6 +13,6 @@ mm=torch.zeros(S,device="cuda"); vv=torch.zeros(S,device="cuda")
 pp=(ctypes.c_void_p*1)(m2._flat.data_ptr()); pg=(ctypes.c_void_p*1)(g.data_ptr())
 for step in (1,2):
     m.apply_gradients(g, step, grad_scale=1/65536.)
-    check(lib.vaenar_adam_step_sharded(ctypes.cast(pp,ctypes.c_void_p), ctypes.cast(pg,ctypes.c_void_p), mm.data_ptr(), vv.data_ptr(), mask.data_ptr(), n, 0, 1, step, 1.25e-4, 0.9, 0.999, 1e-7, 1/65536., torch.cuda.current_stream().cuda_stream))
+    check(lib.vaenar_adam_step_sharded(ctypes.cast(pp,ctypes.c_void_p), ctypes.cast(pg,ctypes.c_void_p), mm.data_ptr(), vv.data_ptr(), mask.data_ptr(), n, 0, 1, step, 1.25e-4, 0.9, 0.999, 1e-7, 1/65536., None, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     print(step, float((m._flat-m2._flat).abs().max()))

@@ -63,14 +63,15 @@ _SIGS = {
     "vaenar_train_step_grads": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                         POINTER(TrainOpts), c_float, c_float, c_float, _P, _P, _P, _P]),
     "vaenar_trainable_mask": (c_int, [_P, _P]),
-    "vaenar_adam_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_float, c_float, c_float, c_float, c_float, _P]),
+    "vaenar_adam_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_float, c_float, c_float, c_float, c_float, _P, _P]),
+    "vaenar_grad_nonfinite": (c_int, [_P, c_int64, _P, _P]),
     "vaenar_enable_peer_access": (c_int, [c_int]),
     "vaenar_ipc_export": (c_int, [_P, _P, POINTER(c_int64)]),
     "vaenar_ipc_open": (c_int, [_P, POINTER(c_void_p)]),
     "vaenar_ipc_close": (c_int, [_P]),
     "vaenar_adam_shard_floats": (c_int64, [c_int64, c_int]),
     "vaenar_adam_step_sharded": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int64, c_float, c_float, c_float, c_float,
-                                         c_float, _P]),
+                                         c_float, _P, _P]),
     "vaenar_crc32c": (ctypes.c_uint32, [_P, c_int64, ctypes.c_uint32]),
     "vaenar_randn": (c_int, [_P, c_int64, c_uint64, c_uint64, c_float, _P]),
     "vaenar_launch_count": (ctypes.c_long, []),

@@ -1710,14 +1710,15 @@ static void inference_one(Ctx& c, const int* texts, const int* t_len, const int*
   c.ws_off = mark;
 }
 
-// VAENAR.inference.  Utterances are independent in inference (BatchNorm uses moving statistics), and most
-// kernels of the chain occupy well under 148 SMs, so the batch is split in two halves that run as two concurrent
-// launch chains (caller stream + an internal side stream, fork/join with events; capturable into one CUDA graph).
+// VAENAR.inference.  One launch chain by default (96 kernels at the LJSpeech shape).  VAENAR_DUAL_CHAIN=1: utterances are
+// independent in inference (BatchNorm uses moving statistics), so the batch can also run as two halves on two concurrent
+// launch chains (caller stream + an internal side stream, fork/join with events; capturable into one CUDA graph) -- that
+// was the faster schedule for the per-op launch chain of round 1; with the fused row kernels both schedules take the same time.
 static void inference_fwd(Ctx& c, const int* texts, const int* t_len, const int* z_len, int B, int Tt, int Tz, int rf,
                           float* z_io, float* text_embd, float* mel, float* ali, float* logp) {
   const vaenar_hparams_t& h = c.m->hp;
-  static const bool single_chain = getenv("VAENAR_SINGLE_CHAIN") != nullptr;   // A/B timing aid
-  const int B0 = (B >= 4 && !single_chain) ? B / 2 : B, B1 = B - B0;
+  static const bool dual_chain = getenv("VAENAR_DUAL_CHAIN") != nullptr;
+  const int B0 = (B >= 4 && dual_chain) ? B / 2 : B, B1 = B - B0;
   const int64_t ali_stride = static_cast<int64_t>(B) * h.dec_heads * Tz * Tt;
   const int64_t mark = c.ws_off;
   if (B1 == 0) {
@@ -2122,21 +2123,30 @@ int vaenar_trainable_mask(vaenar_handle_t h, uint8_t* host_mask) {
   API_END
 }
 
+int vaenar_grad_nonfinite(const float* grads, int64_t n, float* count, void* stream) {
+  API_BEGIN
+  if (!grads || !count) VB_THROW("null argument");
+  nonfinite_count_kernel<<<148 * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(grads, n, count);
+  check_launch("nonfinite_count");
+  API_END
+}
+
 int vaenar_adam_step(float* params, const float* grads, float* m, float* v, const uint8_t* trainable_mask, int64_t n,
-                     int64_t step, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+                     int64_t step, float lr, float beta1, float beta2, float eps, float grad_scale, const float* skip_flag,
+                     void* stream) {
   API_BEGIN
   if (step < 1) VB_THROW("Adam step counts from 1");
   const double lr_t = static_cast<double>(lr) * std::sqrt(1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(step))) /
                       (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(step)));
   adam_step_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      params, grads, m, v, trainable_mask, n, static_cast<float>(lr_t), beta1, beta2, eps, grad_scale);
+      params, grads, m, v, trainable_mask, n, static_cast<float>(lr_t), beta1, beta2, eps, grad_scale, skip_flag);
   check_launch("adam_step");
   API_END
 }
 
 int vaenar_adam_step_sharded(float* const* peer_params, const float* const* peer_grads, float* m_shard, float* v_shard,
                              const uint8_t* trainable_mask, int64_t n, int rank, int world, int64_t step, float lr, float beta1,
-                             float beta2, float eps, float grad_scale, void* stream) {
+                             float beta2, float eps, float grad_scale, const float* skip_flag, void* stream) {
   API_BEGIN
   if (step < 1) VB_THROW("Adam step counts from 1");
   if (world < 1 || world > 8 || rank < 0 || rank >= world) VB_THROW("sharded Adam: rank %d / world %d (max 8)", rank, world);
@@ -2150,7 +2160,7 @@ int vaenar_adam_step_sharded(float* const* peer_params, const float* const* peer
                       (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(step)));
   if (hi > lo) {
     adam_sharded_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(pp, m_shard, v_shard, trainable_mask, lo, hi, rank, world,
-                                                                               static_cast<float>(lr_t), beta1, beta2, eps, grad_scale);
+                                                                               static_cast<float>(lr_t), beta1, beta2, eps, grad_scale, skip_flag);
     check_launch("adam_sharded");
   }
   API_END

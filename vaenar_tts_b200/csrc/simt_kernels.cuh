@@ -495,7 +495,7 @@ __global__ void bn_train_finalize_kernel(const float* __restrict__ partial, int 
     save_mean[c] = static_cast<float>(mean);
     save_rstd[c] = rsqrtf(static_cast<float>(var) + eps);
   }
-  if (update) {
+  if (update && isfinite(mean) && isfinite(var)) {   // an overflowed forward (fp16 operand range) must not poison the moving statistics
     moving_mean[c] = moving_mean[c] * momentum + static_cast<float>(mean) * (1.f - momentum);
     moving_var[c] = moving_var[c] * momentum + static_cast<float>(var) * (1.f - momentum);
   }
@@ -589,9 +589,25 @@ __global__ void randn_kernel(float* __restrict__ out, long n, uint64_t seed, uin
 //   lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr_t m / (sqrt(v) + eps)
 // `trainable` is a per-element byte mask (BatchNorm moving statistics and alignment padding are skipped);
 // grad_scale folds the 1/world_size of the data-parallel gradient mean.
+// Number of non-finite entries of g[0, n) added to *count (fp16 gradient operands in loss-scale space can overflow:
+// the optimiser kernels skip the whole update when the count is non-zero, the host then backs the loss scale off).
+__global__ void nonfinite_count_kernel(const float* __restrict__ g, long n, float* __restrict__ count) {
+  int bad = 0;
+  const long n4 = n / 4;
+  for (long j = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; j < n4; j += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float4 t = *reinterpret_cast<const float4*>(g + j * 4);
+    bad += !isfinite(t.x) + !isfinite(t.y) + !isfinite(t.z) + !isfinite(t.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long i = n4 * 4; i < n; ++i) bad += !isfinite(g[i]);
+  bad = __reduce_add_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(count, static_cast<float>(bad));
+}
+
 __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, const uint8_t* __restrict__ trainable, long n, float lr_t, float b1,
-                                 float b2, float eps, float grad_scale) {
+                                 float b2, float eps, float grad_scale, const float* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag != 0.f) return;   // non-finite gradients somewhere in the job: leave p, m, v untouched
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n || !trainable[i]) return;
   const float gi = g[i] * grad_scale;
@@ -614,7 +630,9 @@ struct PeerPtrs {
 };
 __global__ void __launch_bounds__(256)
 adam_sharded_kernel(const PeerPtrs pp, float* __restrict__ m, float* __restrict__ v, const uint8_t* __restrict__ trainable,
-                    long lo, long hi, int rank, int world, float lr_t, float b1, float b2, float eps, float grad_scale) {
+                    long lo, long hi, int rank, int world, float lr_t, float b1, float b2, float eps, float grad_scale,
+                    const float* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag != 0.f) return;   // identical on every rank (all-reduced count): nobody writes anything
   const long n4 = (hi - lo) / 4;
   for (long j = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; j < n4; j += static_cast<long>(gridDim.x) * blockDim.x) {
     const long i = lo + j * 4;

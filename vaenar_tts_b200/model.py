@@ -54,6 +54,9 @@ def hparams_struct(hps) -> HParamsStruct:
             raise VaenarError(f"{name} attention temperature {temp} != 1.0 is not supported by the fused kernel")
     if getattr(R, "inverse", False):
         raise VaenarError("Prior.inverse=True is not supported (reference configs use inverse=False)")
+    for name, sec in (("Encoder", E), ("Decoder", D)):
+        if getattr(sec, "bn_before_act", False):
+            raise VaenarError(f"{name}.bn_before_act=True is not supported (modules/utils.py:58 default False in all reference configs)")
     return s
 
 
@@ -70,7 +73,9 @@ class _Sub:
 
 
 class VAENAR:
-    def __init__(self, hps, name="VAENAR", device=None, seed=None, **kwargs):
+    def __init__(self, hps, name="VAENAR", device=None, seed=None, noise_seed_offset=0, **kwargs):
+        """``seed`` initialises the parameters (shared by all data-parallel replicas); ``noise_seed_offset`` (e.g. the rank) is
+        mixed into the posterior-noise / dropout streams so that replicas draw different noise for their different data."""
         self.hps = hps
         self.name = name
         self.n_sample = hps.Train.num_samples
@@ -106,6 +111,7 @@ class VAENAR:
         self._ws = None
         self._noise_calls = 0
         self._seed = int(hps.Train.random_seed if seed is None else seed)
+        self._noise_seed = self._seed + 7919 * int(noise_seed_offset)
         self.reset_parameters(self._seed)
         # ---- sub-modules with the reference's attribute names (inference.py:59-72,129-143)
         self.text_encoder = _Sub(self._text_encoder)
@@ -204,7 +210,8 @@ class VAENAR:
     def mark_weights_changed(self):
         self._dirty = True
 
-    def apply_gradients(self, flat_grads, step, lr=None, beta_1=0.9, beta_2=0.999, epsilon=1e-7, grad_scale=1.0):
+    def apply_gradients(self, flat_grads, step, lr=None, beta_1=0.9, beta_2=0.999, epsilon=1e-7, grad_scale=1.0,
+                        skip_flag=None):
         """optimizer.apply_gradients of train.py:137 (Keras Adam, lr 1.25e-4) over the flat gradient buffer, which has
         the layout of the flat parameter buffer.  One fused kernel; Adam moments are created on first use."""
         self._require_cuda()
@@ -220,7 +227,8 @@ class VAENAR:
         lr = float(self.hps.Train.learning_rate if lr is None else lr)
         check(self._lib.vaenar_adam_step(self._p(self._flat), self._p(g), self._p(self._adam_m), self._p(self._adam_v),
                                          self._p(self._trainable_mask), self._flat.numel(), int(step), lr, float(beta_1),
-                                         float(beta_2), float(epsilon), float(grad_scale), self._stream()))
+                                         float(beta_2), float(epsilon), float(grad_scale), self._p(skip_flag),
+                                         self._stream()))
         self._dirty = True
 
     def flat_parameters(self):
@@ -262,7 +270,7 @@ class VAENAR:
     def _noise(self, shape, stddev=1.0):
         out = torch.empty(shape, dtype=torch.float32, device=self.device)
         self._noise_calls += 1
-        check(self._lib.vaenar_randn(self._p(out), out.numel(), self._seed, self._noise_calls, float(stddev),
+        check(self._lib.vaenar_randn(self._p(out), out.numel(), self._noise_seed, self._noise_calls, float(stddev),
                                      self._stream()))
         return out
 
@@ -270,7 +278,7 @@ class VAENAR:
         """vaenar_train_opts_t: injected dropout keep-masks (parity tests) or on-device generation from the seed."""
         o = TrainOpts()
         self._noise_calls += 1
-        o.seed = (self._seed << 20) + self._noise_calls
+        o.seed = (self._noise_seed << 20) + self._noise_calls
         o.update_bn_stats = 1 if update_bn_stats else 0
         keep = None
         if dropout_masks is not None:
@@ -285,8 +293,9 @@ class VAENAR:
     def _no_training(training, what):
         if training:
             raise NotImplementedError(
-                f"{what}(training=True): dropout / batch-statistics BatchNorm and the backward pass are not "
-                "implemented on the CUDA path yet; refusing to silently run inference-mode arithmetic")
+                f"{what}(training=True) as a stand-alone sub-module call is not exposed: training-mode arithmetic (dropout, "
+                "batch-statistics BatchNorm) runs inside VAENAR.__call__(training=True) / train_step / init; refusing to "
+                "silently run inference-mode arithmetic here")
 
     @staticmethod
     def _max_len(lengths):
@@ -434,8 +443,10 @@ class VAENAR:
 
     # ------------------------------------------------------------------ model API (models/models.py)
     def inference(self, inputs, mel_lengths, text_lengths=None, reduction_factor=2, epsilon=None,
-                  return_alignments=True):
-        """VAENAR.inference (models/models.py:199-210) -> (predicted_mel, dec_alignments)."""
+                  return_alignments=True, check_finite=False):
+        """VAENAR.inference (models/models.py:199-210) -> (predicted_mel, dec_alignments).  ``check_finite`` (one host
+        sync): raise instead of returning non-finite mels -- the fp16 tensor-core operands saturate at 65504, which a
+        pathological checkpoint can exceed where the fp32 reference would not."""
         rf = int(reduction_factor)
         texts = self._i32(inputs)
         B, Tt = texts.shape
@@ -459,6 +470,9 @@ class VAENAR:
                                          rf, self._p(z), self._p(emb), self._p(mel), self._p(ali), self._p(logp),
                                          self._stream()))
         self._last = dict(z=z, text_embd=emb, logp=logp)
+        if check_finite and not bool(torch.isfinite(mel).all()):
+            raise VaenarError("inference produced non-finite mel values: an activation exceeded the fp16 operand range "
+                              "(|x| > 65504) of the tensor-core path")
         return mel, self._ali_dict(ali)
 
     def test_step(self, t, t_l, temperature=0.0, return_alignments=True):
@@ -628,31 +642,92 @@ class VAENAR:
         import torch.distributed as dist
         rank, world, group = self._peer
         lr = float(self.hps.Train.learning_rate if lr is None else lr)
-        dist.all_reduce(self._barrier_flag, group=group)          # stream-ordered barrier: every rank's gradients are final
+        # stream-ordered barrier: every rank's gradients are final -- the all-reduced value is the job-wide count of
+        # non-finite gradient entries, so every replica takes the same skip decision
+        dist.all_reduce(self._ovf, group=group)
         check(self._lib.vaenar_adam_step_sharded(
             ctypes.cast(self._peer_params, ctypes.c_void_p), ctypes.cast(self._peer_grads, ctypes.c_void_p),
             self._p(self._shard_m), self._p(self._shard_v), self._p(self._trainable_mask), self._flat.numel(), rank, world,
-            int(step), lr, float(beta_1), float(beta_2), float(epsilon), float(grad_scale), self._stream()))
+            int(step), lr, float(beta_1), float(beta_2), float(epsilon), float(grad_scale), self._p(self._ovf),
+            self._stream()))
         dist.all_reduce(self._barrier_flag, group=group)          # every peer has written its shard into our parameters
         self._dirty = True
 
-    def train_step(self, texts, mels, t_lengths, m_lengths, kl_weight, reduction_factor, eps=None, dropout_masks=None,
-                   loss_scale=None, group=None):
-        """The train_step closure of train.py:120-138: loss, gradients, (data-parallel: ONE all-reduce of the flat
-        gradient buffer over NCCL), Keras Adam.  Returns (loss, mel_l2, kl, length_l2) as a device tensor view."""
+    # ---- dynamic loss scaling (no counterpart in the fp32 reference: the fp16 gradient operands can overflow)
+    MAX_LOSS_SCALE = 65536.0
+    SCALE_GROWTH_INTERVAL = 1000
+
+    @property
+    def loss_scale(self):
+        return float(getattr(self, "_loss_scale", self.DEFAULT_LOSS_SCALE))
+
+    @property
+    def skipped_steps(self):
+        self._poll_overflow(block=True)
+        return int(getattr(self, "_skipped", 0))
+
+    def _poll_overflow(self, block=False):
+        """Consume the overflow counts of finished steps (pinned host copies, no device sync unless ``block``): a step with
+        non-finite gradients was skipped on the device; halve the scale.  After SCALE_GROWTH_INTERVAL clean steps double it."""
+        q = getattr(self, "_ovf_queue", None)
+        if not q:
+            return
+        while q and (block or q[0][0].query()):
+            ev, host = q.pop(0)
+            ev.synchronize()
+            if float(host[0]) != 0.0:
+                self._skipped = getattr(self, "_skipped", 0) + 1
+                self._loss_scale = max(self.loss_scale / 2.0, 1.0)
+                self._good_steps = 0
+            else:
+                self._good_steps = getattr(self, "_good_steps", 0) + 1
+                if self._good_steps >= self.SCALE_GROWTH_INTERVAL and self.loss_scale < self.MAX_LOSS_SCALE:
+                    self._loss_scale = min(self.loss_scale * 2.0, self.MAX_LOSS_SCALE)
+                    self._good_steps = 0
+
+    def exchange_and_apply(self, group=None):
+        """Second half of train_step (train.py:136-137) on the gradients of the last train_step_grads: overflow count,
+        gradient exchange (data-parallel), Keras Adam.  A step whose gradients are not finite anywhere in the job is
+        skipped on every replica (parameters and moments untouched)."""
         import torch.distributed as dist
-        losses, grads = self.train_step_grads(texts, mels, t_lengths, m_lengths, kl_weight, reduction_factor, eps=eps,
-                                              dropout_masks=dropout_masks, loss_scale=loss_scale)
-        world = 1
+        grads = self._grads
+        if getattr(self, "_ovf", None) is None:
+            self._ovf = torch.zeros(1, dtype=torch.float32, device=self.device)
+            self._ovf_queue = []
+        self._ovf.zero_()
         self._opt_step = getattr(self, "_opt_step", 0) + 1
+        S = self._last_loss_scale
         if getattr(self, "_peer", None) is not None:
             # gradient exchange + Adam fused over NVLink peer memory (reduce-scatter -> Adam -> all-gather in one kernel)
-            self._peer_adam(self._opt_step, 1.0 / (self._last_loss_scale * self._peer[1]))
-            return losses[0], losses[1], losses[2], losses[3]
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            world = dist.get_world_size(group)
-            dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=group)      # the single collective of the training path
-        self.apply_gradients(grads, self._opt_step, grad_scale=1.0 / (self._last_loss_scale * world))
+            check(self._lib.vaenar_grad_nonfinite(self._p(grads), grads.numel(), self._p(self._ovf), self._stream()))
+            self._peer_adam(self._opt_step, 1.0 / (S * self._peer[1]))
+        else:
+            world = 1
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                world = dist.get_world_size(group)
+                dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=group)      # the single collective of the training path
+            # after the all-reduce: a non-finite entry of any replica is non-finite in the sum on every replica
+            check(self._lib.vaenar_grad_nonfinite(self._p(grads), grads.numel(), self._p(self._ovf), self._stream()))
+            self.apply_gradients(grads, self._opt_step, grad_scale=1.0 / (S * world), skip_flag=self._ovf)
+        host = torch.empty(1, dtype=torch.float32).pin_memory()
+        host.copy_(self._ovf, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._ovf_queue.append((ev, host))
+        if len(self._ovf_queue) > 64:
+            self._poll_overflow(block=True)
+
+    def train_step(self, texts, mels, t_lengths, m_lengths, kl_weight, reduction_factor, eps=None, dropout_masks=None,
+                   loss_scale=None, group=None):
+        """The train_step closure of train.py:120-138: loss, gradients, (data-parallel: ONE exchange of the flat gradient
+        buffer), Keras Adam.  Returns (loss, mel_l2, kl, length_l2) as device tensor views.  The activation gradients are
+        carried multiplied by a loss scale (default: dynamic, starting at 2^16); a step whose gradients overflow is skipped
+        and the scale halved -- check ``skipped_steps`` / ``loss_scale``."""
+        self._poll_overflow()
+        S = self.loss_scale if loss_scale is None else float(loss_scale)
+        losses, grads = self.train_step_grads(texts, mels, t_lengths, m_lengths, kl_weight, reduction_factor, eps=eps,
+                                              dropout_masks=dropout_masks, loss_scale=S)
+        self.exchange_and_apply(group=group)
         return losses[0], losses[1], losses[2], losses[3]
 
     def init(self, text_inputs, mel_lengths, text_lengths=None, epsilon=None, dropout_masks=None):
@@ -702,17 +777,27 @@ class InferenceSession:
         self.seed = seed
         self.calls = 0
         model._prepare(B, T_text, T_z, rf)
+        # The captured graph bakes in raw pointers: the session owns its workspace (the model's shared one may be
+        # re-allocated by a later call with a larger shape) and keeps the packed-operand arena alive.
+        need = int(model._lib.vaenar_workspace_bytes(model._h, B, T_text, T_z, rf))
+        if need < 0:
+            check(-1)
+        self.ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        self._packed_ref = model._packed
         self.h_texts = torch.zeros(B, T_text, dtype=torch.int32).pin_memory()
         self.h_t_len = torch.ones(B, dtype=torch.int32).pin_memory()
         self.h_z_len = torch.ones(B, dtype=torch.int32).pin_memory()
         self.h_mel = torch.empty(B, T_z * rf, hp.out_dim, dtype=torch.float32).pin_memory()
+        self.h_ali = torch.empty(self.ali.shape, dtype=torch.float32).pin_memory() if return_alignments else None
         self.graph = None
         self.launches_per_call = None
 
     def _launch(self):
         m = self.m
         self.z.copy_(self.eps)
-        check(m._lib.vaenar_inference(m._h, m._p(m._flat), m._p(m._packed), m._p(m._ws), m._ws.numel(),
+        if m._packed is not self._packed_ref:
+            raise VaenarError("the model's packed-operand arena was re-allocated after this session captured its pointer")
+        check(m._lib.vaenar_inference(m._h, m._p(m._flat), m._p(m._packed), m._p(self.ws), self.ws.numel(),
                                       m._p(self.texts), m._p(self.t_len), m._p(self.z_len), self.B, self.Tt, self.Tz,
                                       self.rf, m._p(self.z), m._p(self.emb), m._p(self.mel), m._p(self.ali),
                                       m._p(self.logp), m._stream()))
@@ -757,6 +842,8 @@ class InferenceSession:
         self.z_len.copy_(self.h_z_len, non_blocking=True)
         self.run_device(new_noise)
         self.h_mel.copy_(self.mel, non_blocking=True)
+        if self.h_ali is not None:      # VAENAR.inference returns (mel, alignments) (models/models.py:199-210)
+            self.h_ali.copy_(self.ali, non_blocking=True)
         return self.h_mel
 
     @property
@@ -765,4 +852,4 @@ class InferenceSession:
 
     @property
     def d2h_bytes(self):
-        return self.h_mel.numel() * 4
+        return self.h_mel.numel() * 4 + (self.h_ali.numel() * 4 if self.h_ali is not None else 0)
