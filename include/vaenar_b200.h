@@ -109,6 +109,14 @@ int vaenar_posterior_fwd(vaenar_handle_t h, const float* params, const void* pac
                          const int32_t* z_lengths, const float* eps, int B, int T_text, int T_mel, int T_z, int rf,
                          float* z, float* logq, void* stream);
 
+/* TransformerPosterior.call alone (modules/posterior.py:115-130), training=False: the outputs of mu_projection and
+ * logvar_projection [B, T_z, latent] exactly as the reference returns them (`return mu, logvar, None`, :130).  Note that
+ * VAENAR.call unpacks them swapped (models/models.py:136); this entry point does NOT swap.  reduced_mels [B, T_z, 80]. */
+int vaenar_posterior_params(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
+                            const float* reduced_mels, const float* text_embd, const int32_t* text_lengths,
+                            const int32_t* z_lengths, int B, int T_text, int T_z, float* mu_projection_out,
+                            float* logvar_projection_out, void* stream);
+
 /* TransformerDecoder.call (modules/decoder.py:181-199), training=False: initial / final mel
  * [B, T_z*rf, 80]; alignments (nullable) [dec_nblk, B, heads, T_z, T_text]. */
 int vaenar_decoder_fwd(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
@@ -148,6 +156,13 @@ int vaenar_elbo_fwd_train(vaenar_handle_t h, float* params, const void* packed, 
 int vaenar_init(vaenar_handle_t h, float* params, void* packed, void* ws, int64_t ws_bytes, const int32_t* texts,
                 const int32_t* text_lengths, const int32_t* z_lengths, int B, int T_text, int T_z,
                 const vaenar_train_opts_t* opts, float* z_io, float* mel, void* stream);
+
+/* TransformerPrior.init alone (modules/prior.py:171-186): z_io holds N(0,1) noise on entry and the flow output on return;
+ * every ActNorm's log_scale / bias (modules/flow.py:189-196) is written into `params`, the folded flow maps into `packed`.
+ * Re-pack (vaenar_pack_weights) afterwards. */
+int vaenar_prior_init(vaenar_handle_t h, float* params, void* packed, void* ws, int64_t ws_bytes, const float* text_embd,
+                      const int32_t* text_lengths, const int32_t* z_lengths, int B, int T_text, int T_z, float* z_io,
+                      void* stream);
 
 /* train_step of train.py:120-138 up to the gradients: VAENAR.call(training=True) forward that records what the
  * backward pass needs, the losses (losses[4] = {total, mel_l2, kl, length_l2}, total = mel_l2 + kl_weight * max(kl, 0) +

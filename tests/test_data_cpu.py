@@ -92,5 +92,23 @@ def test_create_dataset_contract(tmp_path):
     shuf = [tuple(b[0]) for b in D.create_dataset(files, 4, 80, shuffle=True, shuffle_buffer=2, seed=3, pin_memory=False)]
     assert sorted(shuf) == sorted(tuple(b[0]) for b in batches)
     parts = [[f for b in D.create_dataset(files, 4, 80, pin_memory=False, shard=(r, 2)) for f in b[0]] for r in range(2)]
-    assert sorted(parts[0] + parts[1]) == sorted(fids) and not set(parts[0]) & set(parts[1])
-    assert parts[0] == fids[0::2] and parts[1] == fids[1::2]
+    assert not set(parts[0]) & set(parts[1])
+    assert parts[0] == fids[0:10:2] and parts[1] == fids[1:10:2]         # 11 utterances: the odd one out is dropped
+
+
+@pytest.mark.parametrize("n_utt,world,bs", [(11, 2, 4), (13, 4, 2), (16, 4, 2), (7, 8, 1), (33, 3, 4)])
+def test_sharded_dataset_same_batch_count_on_every_rank(tmp_path, n_utt, world, bs):
+    """Every train_step issues collectives: all ranks must see the same number of batches (and batch sizes) even when the
+    record count does not divide by world * batch_size -- otherwise the rank with the extra batch deadlocks."""
+    rng = np.random.default_rng(5)
+    utts = [_utt(i, rng) for i in range(n_utt)]
+    p = str(tmp_path / "train-0.tfrecords")
+    D.write_tfrecord(p, [D.serialize_example(*u) for u in utts])
+    per_rank = [[tuple(b[0]) for b in D.create_dataset([p], bs, 80, pin_memory=False, shard=(r, world))] for r in range(world)]
+    sizes = [[len(b) for b in pr] for pr in per_rank]
+    assert all(s == sizes[0] for s in sizes), sizes
+    seen = [f for pr in per_rank for b in pr for f in b]
+    assert len(seen) == len(set(seen)) == n_utt // world * world if n_utt >= world else len(seen) == 0
+    for r in range(world):
+        flat = [f for b in per_rank[r] for f in b]
+        assert flat == [u[0] for u in utts[:n_utt // world * world]][r::world] or sizes[0] == []

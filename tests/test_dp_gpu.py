@@ -18,6 +18,15 @@ def _free_port():
 
 
 def _worker(rank, world, port, q):
+    try:
+        _worker_body(rank, world, port, q)
+    except Exception as e:   # report instead of leaving the parent in q.get until its timeout
+        import traceback
+        q.put((rank, "error", traceback.format_exc()[-2000:]))
+        raise
+
+
+def _worker_body(rank, world, port, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
@@ -56,7 +65,10 @@ def test_two_gpu_train_step_allreduce():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=600) for _ in range(world))
+    res = [q.get(timeout=300) for _ in range(world)]
+    for r in res:
+        assert r[1] != "error", r[2]
+    res = sorted(res)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -69,6 +81,15 @@ def test_two_gpu_train_step_allreduce():
 
 
 def _peer_worker(rank, world, port, q):
+    try:
+        _peer_worker_body(rank, world, port, q)
+    except Exception as e:
+        import traceback
+        q.put((rank, "error", traceback.format_exc()[-2000:]))
+        raise
+
+
+def _peer_worker_body(rank, world, port, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
@@ -119,7 +140,10 @@ def test_two_gpu_peer_memory_optimizer_matches_allreduce_adam():
     procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=600) for _ in range(world))
+    res = [q.get(timeout=300) for _ in range(world)]
+    for r in res:
+        assert r[1] != "error", r[2]
+    res = sorted(res)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0

@@ -1,6 +1,8 @@
 """Parity of the CUDA path, called through the C ABI behind the reference-shaped VAENAR API, against
 (a) the golden vectors produced by the reference's own sources (tests/golden) and (b) the CPU oracle.
 Tolerances are the north-star ones: mel MAE <= 1e-3, KL / loss relative difference <= 1e-3."""
+import os
+
 import pytest
 import torch
 
@@ -230,3 +232,83 @@ def test_inference_py_test_step_vs_oracle():
     assert mel.shape == ref.shape
     assert masked_mae(mel, ref, reduced * 2) <= MEL_MAE_TOL
     assert set(ali) == {"decoder-attention-0", "decoder-attention-1"}
+
+
+@pytest.mark.parametrize("case", list(CASES)[:2])
+def test_posterior_facade_reference_shape(case):
+    """model.posterior(...) -> (mu, logvar, None) exactly like TransformerPosterior.call (modules/posterior.py:115-130, NOT
+    swapped), + reparameterize / log_probability (posterior.py:20-72) against the oracle; the fused path VAENAR.call uses
+    (posterior.sample_fused, models.py:136 swap applied) must agree with composing the three."""
+    ohps, g, P = load_case(case)
+    m = make_model(ohps, P)
+    t_len, m_len = t(g, "t_len"), t(g, "m_len")
+    rf = int(g["rf"])
+    mels = t(g, "mels")
+    reduced = mels[:, ::rf]
+    z_len = (m_len + rf - 1) // rf
+    with torch.no_grad():
+        emb = O.text_encoder(P, ohps, t(g, "texts"), t_len, ohps.Common.mel_text_len_ratio / float(rf))
+        ref_mu, ref_lv = O.posterior(P, ohps, reduced, emb, t_len, z_len)
+    mu, logvar, none = m.posterior(reduced, emb, src_lengths=t_len, target_lengths=z_len, training=False)
+    assert none is None
+    mask = O.sequence_mask(z_len, mu.shape[1], torch.float32)[:, :, None]
+    assert float(((mu.cpu() - ref_mu).abs() * mask).max()) < 5e-3
+    assert float(((logvar.cpu() - ref_lv).abs() * mask).max()) < 5e-3
+    # models.py:136: `logvar, mu, _ = self.posterior(...)` -> the mean is the logvar_projection output
+    eps = torch.randn(mu.shape[0], 1, mu.shape[1], mu.shape[2], generator=torch.Generator().manual_seed(1))
+    samples, eps_out = m.posterior.reparameterize(logvar, mu, nsamples=1, eps=eps)
+    logq = m.posterior.log_probability(logvar, mu, eps=eps_out, seq_lengths=z_len)
+    with torch.no_grad():
+        ref_z = O.reparameterize(ref_lv, ref_mu, eps)
+        ref_logq = O.posterior_log_probability(ref_lv, ref_mu, eps, z_len)
+    assert float(((samples.cpu() - ref_z)[:, 0].abs() * mask).max()) < 1e-2
+    assert rel(logq[:, 0], ref_logq[:, 0]) < REL_TOL
+    z_f, logq_f = m.posterior.sample_fused(reduced, emb, src_lengths=t_len, target_lengths=z_len, eps=eps[:, 0])
+    assert float(((z_f.cpu() - samples[:, 0].cpu()).abs() * mask).max()) < 1e-5
+    assert rel(logq_f, logq[:, 0].cpu()) < 1e-5
+
+
+def test_prior_init_standalone_matches_oracle():
+    """model.prior.init (modules/prior.py:171-186) as a stand-alone sub-module call: data-dependent ActNorm parameters and
+    the flow output against the oracle's prior_sample(init=True)."""
+    from oracle.hparams import LJHPS as OLJ2
+    P = O.init_params(OLJ2, seed=71, zero_init_std=0.02)
+    m = make_model(OLJ2, P)
+    texts, _, t_len, m_len = O.synthetic_batch(OLJ2, 3, 20, 100, rf=5, seed=72)
+    z_len = (m_len + 4) // 5
+    eps = torch.randn(3, int(z_len.max()), 128, generator=torch.Generator().manual_seed(73))
+    with torch.no_grad():
+        emb = O.text_encoder(P, OLJ2, texts, t_len, OLJ2.Common.mel_text_len_ratio / 5.0)
+        Pi = {k: v.clone() for k, v in P.items()}
+        zr, _ = O.prior_sample(Pi, OLJ2, eps, z_len, emb, t_len, init=True)
+    z, logp = m.prior.init(z_len, emb, t_len, epsilon=eps)
+    torch.cuda.synchronize()
+    sd = m.state_dict()
+    for s in range(OLJ2.Prior.n_blk):
+        for nme in ("log_scale", "bias"):
+            k = f"prior.glow.{s}.actnorm.{nme}"
+            assert float((sd[k].cpu() - Pi[k]).abs().max()) < 2e-2, k
+    zmask = O.sequence_mask(z_len, z.shape[1], torch.float32)[:, :, None]
+    assert float(((z.cpu() - zr).abs() * zmask).mean()) < 5e-3
+    assert torch.isfinite(logp).all()
+
+
+def test_inference_test_loop_rtf_and_mel_writer(tmp_path):
+    """inference.py:145-168 + audio/utils.py:16-22: RTF accounting over test_step and one .npy per utterance."""
+    import numpy as np
+    from vaenar_tts_b200.synthesis import inference_test
+    P = O.init_params(OLJ, seed=31, zero_init_std=0.02)
+    P["length_predictor.projection.bias"] = torch.tensor([1.0])
+    m = make_model(OLJ, P)
+    batches = []
+    for i in range(2):
+        texts, _, t_len, _ = O.synthetic_batch(OLJ, 2, 20, 80, seed=40 + i)
+        batches.append(([f"utt{i}a".encode(), f"utt{i}b"], texts, t_len))
+    out = inference_test(m, batches, frame_shift_sample=256, sample_rate=22050, save_dir=str(tmp_path), ckpt_step=7,
+                         write_mel_files=True)
+    assert out["n_utterances"] == 4 and out["time_consumed"] > 0 and out["durations"] > 0
+    assert abs(out["average_rtf"] - out["time_consumed"] / out["durations"]) < 1e-12
+    files = sorted(os.listdir(tmp_path))
+    assert files == sorted(f"prior-utt{i}{c}-7.npy" for i in range(2) for c in "ab")
+    mel = np.load(os.path.join(tmp_path, files[0]))
+    assert mel.ndim == 2 and mel.shape[1] == 80 and np.isfinite(mel).all()

@@ -1,5 +1,6 @@
-"""world_size-2 gloo tests (CPU) of the data-parallel host logic: utterance sharding, the single gradient
-all-reduce, and the max-over-ranks / whole-job aggregation bench.py uses."""
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: utterance sharding (batch tensors and the sharded
+TFRecord dataset: same batch count on every rank), the parameter broadcast, the all-reduced overflow count that makes every
+replica skip the same train step, and the max-over-ranks timing reduction bench.py uses."""
 import os
 import socket
 
@@ -26,9 +27,18 @@ def _worker(rank, world, port, out):
     mine = P.shard_batch([texts, mels, t_len, m_len], rank, world)
     ids = P.shard_utterances(6, rank, world)
     g = torch.full((1000,), float(rank + 1))
-    P.allreduce_mean_(g)
-    tmax = P.max_over_ranks(1.0 + rank)
-    frames = P.gather_frames(int(mine[3].sum()))
+    dist.all_reduce(g)                           # the single collective of the training path (sum; Adam folds 1 / world)
+    g /= world
+    tt = torch.tensor([1.0 + rank], dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)    # bench.py: a multi-GPU time is the max over ranks
+    tmax = float(tt)
+    fr = torch.tensor([int(mine[3].sum())])
+    dist.all_reduce(fr)
+    frames = int(fr)
+    # overflow guard: only rank 1 sees a non-finite gradient; the all-reduced count makes BOTH ranks skip the step
+    ovf = torch.tensor([1.0 if rank == 1 else 0.0])
+    dist.all_reduce(ovf)
+    assert float(ovf) == 1.0
     # replicas start from rank 0's parameters (host logic of VAENAR.broadcast_parameters, here over gloo on CPU tensors)
     import __graft_entry__ as ge
     ge.build()

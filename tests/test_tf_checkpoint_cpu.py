@@ -81,7 +81,8 @@ def test_state_dict_roundtrip_through_bundle(tmp_path):
     back = C.load_tf_checkpoint(prefix)
     assert set(back) == set(sd)
     for k, v in sd.items():
-        assert back[k].shape == tuple(v.shape) and np.array_equal(back[k], v.numpy()), k
+        want = () if k.endswith("pos_weight") else tuple(v.shape)      # TF scalars (tf.Variable(1.0)) have shape []
+        assert back[k].shape == want and np.array_equal(back[k].reshape(v.shape), v.numpy()), k
     m2 = VAENAR(LJHPS, device="cpu", seed=4)
     m2.load_state_dict(back)
     assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
@@ -91,3 +92,29 @@ def test_state_dict_roundtrip_through_bundle(tmp_path):
     open(prefix + ".data-00000-of-00001", "wb").write(data)
     with pytest.raises(ValueError):
         C.read_bundle(prefix)
+
+
+def test_optimizer_state_and_step_survive_a_checkpoint(tmp_path):
+    """train.py:246 checkpoints (step, optimizer, model): the Adam moments and the optimizer iteration must come back, so that
+    a resumed run continues the bias correction instead of restarting at t = 1 with zero moments."""
+    import __graft_entry__ as g
+    g.build()
+    from vaenar_tts_b200 import VAENAR, LJHPS
+    m = VAENAR(LJHPS, device="cpu", seed=3)
+    m._ensure_adam_state()
+    gen = torch.Generator().manual_seed(0)
+    m._adam_m.copy_(torch.randn(m._adam_m.shape, generator=gen) * m._trainable_mask.float())
+    m._adam_v.copy_(torch.rand(m._adam_v.shape, generator=gen) * m._trainable_mask.float())
+    m._opt_step = 1234
+    prefix = str(tmp_path / "ckpt-3")
+    m.save_tf_checkpoint(prefix, step=3)
+    raw = C.read_bundle(prefix)
+    assert raw["optimizer/iter/.ATTRIBUTES/VARIABLE_VALUE"].shape == () and int(raw["optimizer/iter/.ATTRIBUTES/VARIABLE_VALUE"]) == 1234
+    assert raw["model/text_encoder/pos_weight/.ATTRIBUTES/VARIABLE_VALUE"].shape == ()
+    key = "model/decoder/pre_projection/kernel/.OPTIMIZER_SLOT/optimizer/m/.ATTRIBUTES/VARIABLE_VALUE"
+    assert key in raw and raw[key].shape == (128, 256)
+    m2 = VAENAR(LJHPS, device="cpu", seed=9)
+    m2.load_tf_checkpoint(prefix)
+    assert m2._opt_step == 1234
+    assert torch.equal(m2._adam_m, m._adam_m) and torch.equal(m2._adam_v, m._adam_v)
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))

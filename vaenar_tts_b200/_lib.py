@@ -51,6 +51,7 @@ _SIGS = {
     "vaenar_prior_log_probability": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "vaenar_posterior_fwd": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                      _P, _P, _P]),
+    "vaenar_posterior_params": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "vaenar_decoder_fwd": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "vaenar_inference": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P,
                                  _P]),
@@ -59,6 +60,7 @@ _SIGS = {
     "vaenar_elbo_fwd_train": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                       POINTER(TrainOpts), _P, _P, _P, _P, _P, _P]),
     "vaenar_init": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, POINTER(TrainOpts), _P, _P, _P]),
+    "vaenar_prior_init": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "vaenar_train_workspace_bytes": (c_int64, [_P, c_int, c_int, c_int, c_int]),
     "vaenar_train_step_grads": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                         POINTER(TrainOpts), c_float, c_float, c_float, _P, _P, _P, _P]),

@@ -205,6 +205,11 @@ static void add_xblk(vaenar_model& m, const std::string& n, int d, int mem, int 
 }
 
 static int kpad64(int k) { return cdiv(k, 64) * 64; }
+// tuning aid: the first VAENAR_POST_PLAIN PostNet convolutions run on plain fp16 operands instead of split-fp16 (inference only)
+static int post_plain() {
+  static const int v = getenv("VAENAR_POST_PLAIN") ? atoi(getenv("VAENAR_POST_PLAIN")) : 0;
+  return v;
+}
 
 // packed operand plan of one CrossAttentionBLK (modules/attention.py:418-452)
 static void plan_xblk(vaenar_model& m, const std::string& pk, const std::string& n, int d, int ffn) {
@@ -430,7 +435,7 @@ static void build_model(vaenar_model& m) {
     int cin = O;
     for (int i = 0; i < h.post_n_conv; ++i) {
       plan_conv(m, "dec.post" + std::to_string(i), "decoder.postnet.conv_stack." + std::to_string(i), h.post_kernel, cin,
-                h.post_filters, true);
+                h.post_filters, i >= post_plain());
       cin = h.post_filters;
     }
   }
@@ -1509,7 +1514,8 @@ static void prior_logprob(Ctx& c, const float* z_in, const float* text_embd, con
 
 // TransformerPosterior.call + reparameterize + log_probability (modules/posterior.py:20-72,115-130)
 static void posterior_fwd(Ctx& c, const float* mels, const float* text_embd, const int* t_len, const int* z_len,
-                          const float* eps, int B, int Tt, int Tm, int Tz, int rf, float* z, float* logq) {
+                          const float* eps, int B, int Tt, int Tm, int Tz, int rf, float* z, float* logq,
+                          float* save_lv = nullptr) {
   const vaenar_hparams_t& h = c.m->hp;
   const int d = h.posterior_att_dim, H = h.posterior_heads, F = h.posterior_ffn, E = h.enc_hidden, L = h.latent_dim,
             O = h.out_dim;
@@ -1578,6 +1584,7 @@ static void posterior_fwd(Ctx& c, const float* mels, const float* text_embd, con
     p.mode = EPI_POSTERIOR; p.N = 2 * L; segs_plain(p, d);
     p.seq_T = Tz; p.seq_B = B;
     p.bias = c.V("post.out.bias"); p.eps_in = eps; p.z = z; p.z_h = zh; p.z_ld = L; p.row_acc = row_acc; p.lengths = z_len;
+    p.save_lv = save_lv;
     run_gemm(c, 2 * L, AOp{x.h, d, d}, AOp{}, 1, static_cast<int>(rows), c.W("post.out"), d, 2 * L, p);
   }
   if (!c.dry) {
@@ -1634,8 +1641,9 @@ static void decoder_fwd(Ctx& c, const float* z, const float* text_embd, const in
   const int post_bn = post_bn_env ? post_bn_env : 256;
   for (int i = 0; i < h.post_n_conv; ++i) {
     const std::string pk = "dec.post" + std::to_string(i), pn = "decoder.postnet.conv_stack." + std::to_string(i);
-    conv_bn(c, pk, pn, AOp{in_h, cin, cin}, AOp{in_l, cin, cin}, B, Tm, cin, C, h.post_kernel,
-            (i < h.post_n_conv - 1) ? 2 : 0, true, post_bn, h.post_drop_rate, out_h, out_l);
+    const bool split = i >= post_plain();
+    conv_bn(c, pk, pn, AOp{in_h, cin, cin}, split ? AOp{in_l, cin, cin} : AOp{}, B, Tm, cin, C, h.post_kernel,
+            (i < h.post_n_conv - 1) ? 2 : 0, split, post_bn, h.post_drop_rate, out_h, out_l);
     in_h = out_h; in_l = out_l;
     out_h = (in_h == pa_h) ? pb_h : pa_h;
     out_l = (in_l == pa_l) ? pb_l : pa_l;
@@ -2016,6 +2024,23 @@ int vaenar_posterior_fwd(vaenar_handle_t h, const float* params, const void* pac
   API_END
 }
 
+int vaenar_posterior_params(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
+                            const float* reduced_mels, const float* text_embd, const int32_t* text_lengths,
+                            const int32_t* z_lengths, int B, int T_text, int T_z, float* mu_projection_out,
+                            float* logvar_projection_out, void* stream) {
+  API_BEGIN
+  Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
+  // the fused epilogue computes z = eps * exp(lv / 2) + mean with lv = mu_projection output, mean = logvar_projection
+  // output (models/models.py:136): with eps = 0, z is the logvar_projection output and the saved lv the mu_projection's
+  const int64_t n = static_cast<int64_t>(B) * T_z * h->hp.latent_dim;
+  float* zero = c.alloc<float>(n);
+  float* logq = c.alloc<float>(B);
+  VB_CUDA(cudaMemsetAsync(zero, 0, n * sizeof(float), c.stream));
+  posterior_fwd(c, reduced_mels, text_embd, text_lengths, z_lengths, zero, B, T_text, T_z, T_z, 1, logvar_projection_out, logq,
+                mu_projection_out);
+  API_END
+}
+
 int vaenar_decoder_fwd(vaenar_handle_t h, const float* params, const void* packed, void* ws, int64_t ws_bytes,
                        const float* z, const float* text_embd, const int32_t* z_lengths,
                        const int32_t* text_lengths, int B, int T_text, int T_z, int rf, float* initial_mel,
@@ -2077,6 +2102,16 @@ int vaenar_init(vaenar_handle_t h, float* params, void* packed, void* ws, int64_
   Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
   apply_train_opts(c, params, opts);
   init_fwd(c, texts, text_lengths, z_lengths, B, T_text, T_z, z_io, mel);
+  API_END
+}
+
+int vaenar_prior_init(vaenar_handle_t h, float* params, void* packed, void* ws, int64_t ws_bytes, const float* text_embd,
+                      const int32_t* text_lengths, const int32_t* z_lengths, int B, int T_text, int T_z, float* z_io,
+                      void* stream) {
+  API_BEGIN
+  Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream);
+  c.params_mut = params;
+  prior_init(c, text_embd, text_lengths, z_lengths, B, T_text, T_z, z_io);
   API_END
 }
 

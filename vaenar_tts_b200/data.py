@@ -215,19 +215,28 @@ def padded_batch(items, num_mels, pin_memory=True):
 def create_dataset(tfrecord_files, batch_size, num_mels, pad_factor=0, num_parallel_reads=1, shuffle=False,
                    shuffle_buffer=128, seed=1, pin_memory=True, shard=None):
     """``TFRecordWriter.create_dataset`` (tf_record_utils.py:126-142) as a generator of padded batches.
-    ``shard=(rank, world)`` keeps every world-th utterance starting at ``rank`` (the reference's own multi-worker rule
-    ``utt_ids[rank::size]``, datasets/datasets.py:179-192) BEFORE batching -- data-parallel training."""
+    ``shard=(rank, world)``: data-parallel training.  The stream is cut into GLOBAL batches of ``batch_size * world``
+    utterances and rank r takes every world-th utterance of each global batch starting at r (the reference's own
+    multi-worker rule ``utt_ids[rank::size]``, datasets/datasets.py:179-192, applied per global batch).  Every rank
+    therefore yields the SAME number of batches of the SAME size -- each train_step issues collectives, unequal batch
+    counts would deadlock at the end of an epoch; the tail that does not divide by ``world`` is dropped."""
     def batches():
+        if shard is None:
+            rank, world = 0, 1
+        else:
+            rank, world = int(shard[0]), int(shard[1])
+            if not (0 <= rank < world):
+                raise ValueError(f"shard=(rank {rank}, world {world})")
         cur = []
-        for i, rec in enumerate(iter_records(tfrecord_files, num_parallel_reads)):
-            if shard is not None and i % shard[1] != shard[0]:
-                continue
-            cur.append(parse_example(rec, pad_factor))
-            if len(cur) == batch_size:
-                yield padded_batch(cur, num_mels, pin_memory)
+        for rec in iter_records(tfrecord_files, num_parallel_reads):
+            cur.append(rec)
+            if len(cur) == batch_size * world:
+                yield padded_batch([parse_example(r, pad_factor) for r in cur[rank::world]], num_mels, pin_memory)
                 cur = []
+        if world > 1:
+            cur = cur[:len(cur) // world * world]                 # same batch count and size on every rank
         if cur:
-            yield padded_batch(cur, num_mels, pin_memory)          # padded_batch keeps the final partial batch
+            yield padded_batch([parse_example(r, pad_factor) for r in cur[rank::world]], num_mels, pin_memory)   # final partial batch kept
     if not shuffle:
         yield from batches()
         return

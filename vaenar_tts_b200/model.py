@@ -117,7 +117,8 @@ class VAENAR:
         self.text_encoder = _Sub(self._text_encoder)
         self.length_predictor = _Sub(self._length_predictor)
         self.decoder = _Sub(self._decoder)
-        self.posterior = _Sub(self._posterior)
+        self.posterior = _Sub(self._posterior, reparameterize=self._posterior_reparameterize,
+                              log_probability=self._posterior_log_probability, sample_fused=self._posterior_sample)
         self.prior = _Sub(self._prior_sample, sample=self._prior_sample, log_probability=self._prior_log_probability,
                           init=self._prior_init)
 
@@ -184,17 +185,54 @@ class VAENAR:
                     v.copy_(src.reshape(v.shape))
         self._dirty = True
 
-    def load_tf_checkpoint(self, prefix, strict=True):
+    def load_tf_checkpoint(self, prefix, strict=True, restore_optimizer=True):
         """Restore the model weights from a TF2 object-graph checkpoint written by the reference
-        (``tf.train.Checkpoint(model=...)``, train.py:246-248 / inference.py:39-41): ``prefix`` = ``.../ckpt-N``.
-        TensorFlow is not needed (vaenar_tts_b200/tf_checkpoint.py)."""
+        (``tf.train.Checkpoint(step=, optimizer=, model=)``, train.py:246-248 / inference.py:39-41): ``prefix`` =
+        ``.../ckpt-N``; when the checkpoint carries them, also the Adam moments and the optimizer's iteration count
+        (a resumed run continues the bias correction instead of restarting at t = 1).  TensorFlow is not needed
+        (vaenar_tts_b200/tf_checkpoint.py)."""
         from . import tf_checkpoint
-        self.load_state_dict(tf_checkpoint.load_tf_checkpoint(prefix), strict=strict)
+        sd = tf_checkpoint.load_tf_checkpoint(prefix)
+        if any(v.ndim == 0 for v in sd.values()):
+            sd = {k: (v.reshape(1) if v.ndim == 0 else v) for k, v in sd.items()}     # TF scalars have shape []
+        self.load_state_dict(sd, strict=strict)
+        if restore_optimizer:
+            m, v, it = tf_checkpoint.load_tf_optimizer_state(prefix)
+            if m and v:
+                self._ensure_adam_state()
+                for n, shape, off, tr in self._manifest:
+                    if tr and n in m and n in v:
+                        numel = int(math.prod(shape))
+                        self._adam_m[off:off + numel].copy_(torch.as_tensor(m[n], dtype=torch.float32).reshape(-1))
+                        self._adam_v[off:off + numel].copy_(torch.as_tensor(v[n], dtype=torch.float32).reshape(-1))
+            if it is not None:
+                self._opt_step = int(it)
 
     def save_tf_checkpoint(self, prefix, step=0):
-        """Write the weights under the reference's checkpoint keys (tensor-bundle format)."""
+        """Write what ``tf.train.Checkpoint(step=, optimizer=, model=)`` persists (train.py:246): the weights under the
+        reference's checkpoint keys, the Adam moments as optimizer slots and the optimizer iteration count."""
         from . import tf_checkpoint
-        tf_checkpoint.save_tf_checkpoint(prefix, self.state_dict(), step=step)
+        m = v = None
+        if hasattr(self, "_adam_m"):
+            m, v = {}, {}
+            for n, shape, off, tr in self._manifest:
+                if tr:
+                    numel = int(math.prod(shape))
+                    m[n] = self._adam_m[off:off + numel].view(shape)
+                    v[n] = self._adam_v[off:off + numel].view(shape)
+        elif getattr(self, "_peer", None) is not None:
+            raise VaenarError("save_tf_checkpoint with the sharded peer optimizer: gather the moment shards first "
+                              "(each rank holds 1/world of Adam's m and v)")
+        tf_checkpoint.save_tf_checkpoint(prefix, self.state_dict(), step=step, adam_m=m, adam_v=v,
+                                         opt_step=getattr(self, "_opt_step", None))
+
+    def _ensure_adam_state(self):
+        if not hasattr(self, "_adam_m"):
+            self._adam_m = torch.zeros_like(self._flat)
+            self._adam_v = torch.zeros_like(self._flat)
+            host = torch.zeros(self._flat.numel(), dtype=torch.uint8)
+            check(self._lib.vaenar_trainable_mask(self._h, ctypes.c_void_p(host.data_ptr())))
+            self._trainable_mask = host.to(self.device)
 
     @property
     def trainable_variables(self):
@@ -218,12 +256,7 @@ class VAENAR:
         g = self._f32(flat_grads)
         if g.numel() != self._flat.numel():
             raise VaenarError("gradient buffer must have the flat parameter layout")
-        if not hasattr(self, "_adam_m"):
-            self._adam_m = torch.zeros_like(self._flat)
-            self._adam_v = torch.zeros_like(self._flat)
-            host = torch.zeros(self._flat.numel(), dtype=torch.uint8)
-            check(self._lib.vaenar_trainable_mask(self._h, ctypes.c_void_p(host.data_ptr())))
-            self._trainable_mask = host.to(self.device)
+        self._ensure_adam_state()
         lr = float(self.hps.Train.learning_rate if lr is None else lr)
         check(self._lib.vaenar_adam_step(self._p(self._flat), self._p(g), self._p(self._adam_m), self._p(self._adam_v),
                                          self._p(self._trainable_mask), self._flat.numel(), int(step), lr, float(beta_1),
@@ -366,16 +399,74 @@ class VAENAR:
                                                      self._stream()))
         return logp
 
-    def _prior_init(self, *a, **kw):
-        raise NotImplementedError("prior.init (modules/prior.py:171-186) is only reachable through VAENAR.init "
-                                  "(models/models.py:212-226), which runs it fused with the encoder / decoder passes")
+    def _prior_init(self, targets_lengths, condition_inputs, condition_lengths=None, training=None, epsilon=None):
+        """TransformerPrior.init (modules/prior.py:171-186): data-dependent ActNorm initialisation of every flow step from
+        an N(0,1) sample pushed through the flow; writes actnorm.log_scale / bias, returns (z, logp) like ``sample``.
+        The reference only reaches it through VAENAR.init; as a stand-alone call it needs the text encoding."""
+        emb = self._f32(condition_inputs)
+        B, Tt, _ = emb.shape
+        Tz = self._max_len(targets_lengths)
+        z_len = self._i32(targets_lengths)
+        t_len = self._i32(condition_lengths)
+        self._prepare(B, Tt, Tz, 1)
+        L = self._hp.latent_dim
+        z = self._noise((B, Tz, L)) if epsilon is None else self._f32(epsilon).contiguous().clone()
+        check(self._lib.vaenar_prior_init(self._h, self._p(self._flat), self._p(self._packed), self._p(self._ws),
+                                          self._ws.numel(), self._p(emb), self._p(t_len), self._p(z_len), B, Tt, Tz,
+                                          self._p(z), self._stream()))
+        self._dirty = True                  # ActNorm parameters changed: operands are re-packed on the next call
+        return z, self._prior_log_probability(z, emb, z_len, t_len)
 
-    def _posterior(self, inputs, src_enc, src_lengths=None, target_lengths=None, training=None, eps=None,
-                   reduction_factor=None, full_mels=None):
-        """TransformerPosterior.call fused with reparameterize + log_probability
-        (modules/posterior.py:20-72,115-130): ``inputs`` are the reduced mels [B,T_z,80]; returns (z, logq)."""
+    def _posterior(self, inputs, src_enc, src_lengths=None, target_lengths=None, training=None):
+        """TransformerPosterior.call (modules/posterior.py:115-130) -> (mu, logvar, None): the outputs of mu_projection
+        and logvar_projection, NOT swapped (VAENAR.call swaps them when unpacking, models/models.py:136).  ``inputs`` are
+        the reduced mels [B, T_z, 80]."""
         self._no_training(training, "posterior")
         rm = self._f32(inputs)
+        emb = self._f32(src_enc)
+        B, Tz, _ = rm.shape
+        Tt = emb.shape[1]
+        z_len = self._i32(target_lengths) if target_lengths is not None else torch.full((B,), Tz, dtype=torch.int32, device=self.device)
+        t_len = self._i32(src_lengths) if src_lengths is not None else torch.full((B,), Tt, dtype=torch.int32, device=self.device)
+        L = self._hp.latent_dim
+        self._prepare(B, Tt, Tz, 1)
+        mu = torch.empty(B, Tz, L, dtype=torch.float32, device=self.device)
+        logvar = torch.empty_like(mu)
+        check(self._lib.vaenar_posterior_params(self._h, self._p(self._flat), self._p(self._packed), self._p(self._ws),
+                                                self._ws.numel(), self._p(rm), self._p(emb), self._p(t_len), self._p(z_len),
+                                                B, Tt, Tz, self._p(mu), self._p(logvar), self._stream()))
+        return mu, logvar, None
+
+    def _posterior_reparameterize(self, mu, logvar, nsamples=1, random=True, eps=None):
+        """BasePosterior.reparameterize (modules/posterior.py:20-39) -> (samples, eps) [B, nsamples, T, dim].  Facade helper on
+        device tensors (elementwise); VAENAR.__call__ / train_step use the fused GEMM epilogue instead."""
+        mu, logvar = self._f32(mu), self._f32(logvar)
+        B, T, D = mu.shape
+        n = int(nsamples)
+        if eps is None:
+            eps = self._noise((B, n, T, D)) if random else torch.zeros(B, n, T, D, dtype=torch.float32, device=self.device)
+        else:
+            eps = self._f32(eps).reshape(B, n, T, D)
+        return eps * torch.exp(0.5 * logvar)[:, None] + mu[:, None], eps
+
+    def _posterior_log_probability(self, mu, logvar, z=None, eps=None, seq_lengths=None, epsilon=1e-8):
+        """BasePosterior.log_probability (modules/posterior.py:41-72) -> [B, nsamples]."""
+        mu, logvar = self._f32(mu), self._f32(logvar)
+        B, T, D = mu.shape
+        if eps is not None:
+            ns = self._f32(eps)
+        else:
+            ns = (self._f32(z) - mu[:, None]) / (torch.exp(0.5 * logvar)[:, None] + float(epsilon))
+        tl = -0.5 * (D * math.log(2 * math.pi) + (logvar[:, None] + ns ** 2).sum(-1))
+        if seq_lengths is not None:
+            mask = (torch.arange(T, device=self.device)[None, :] < self._i32(seq_lengths)[:, None]).float()
+            tl = tl * mask[:, None]
+        return tl.sum(-1)
+
+    def _posterior_sample(self, reduced_mels, src_enc, src_lengths=None, target_lengths=None, eps=None):
+        """The fused path VAENAR.call uses: posterior + reparameterize + log_probability (one GEMM epilogue), with the
+        (logvar, mu) swap of models/models.py:136 applied -> (z [B,T_z,latent], logq [B])."""
+        rm = self._f32(reduced_mels)
         emb = self._f32(src_enc)
         B, Tz, _ = rm.shape
         Tt = emb.shape[1]
@@ -693,6 +784,7 @@ class VAENAR:
         grads = self._grads
         if getattr(self, "_ovf", None) is None:
             self._ovf = torch.zeros(1, dtype=torch.float32, device=self.device)
+        if getattr(self, "_ovf_queue", None) is None:
             self._ovf_queue = []
         self._ovf.zero_()
         self._opt_step = getattr(self, "_opt_step", 0) + 1

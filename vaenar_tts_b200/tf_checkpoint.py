@@ -1,7 +1,9 @@
 """TensorFlow-free reader / writer of TF2 object-graph checkpoints (the "tensor bundle" format) for the VAENAR weights
 -- SURVEY.md §8f rank 1: lets the checkpoints written by the reference (``tf.train.Checkpoint(step=, optimizer=, model=)``,
 train.py:246-248, restored by inference.py:39-41,122-123) be loaded into ``vaenar_tts_b200.VAENAR.load_state_dict`` and
-the trained weights of this implementation be written back in a form ``tf.train.Checkpoint.restore`` can read.
+the trained weights + Adam state of this implementation be written back under the same keys.  No
+``_CHECKPOINTABLE_OBJECT_GRAPH`` proto is written, so ``tf.train.Checkpoint.restore`` can NOT read the files this module
+writes; ``tf.train.load_checkpoint(prefix).get_tensor(key)`` (name-based) can.
 
 Format (public, stable since TF 1.x; restated from tensorflow/core/util/tensor_bundle and the LevelDB table format):
 
@@ -310,10 +312,46 @@ def load_tf_checkpoint(prefix):
     return sd
 
 
-def save_tf_checkpoint(prefix, state_dict, step=0):
-    """Write the model weights under the reference's object-graph keys (+ the ``step`` counter of train.py:246).
-    No object-graph proto is written: restore with ``tf.train.load_checkpoint`` / name-based assignment."""
-    tensors = {name_to_tf_key(k): np.asarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v, dtype=np.float32)
-               for k, v in state_dict.items()}
+def _slot_key(name: str, slot: str):
+    """Keras optimizer slot of a model variable in the object graph: ``model/<path>/.OPTIMIZER_SLOT/optimizer/<m|v>/...``"""
+    return name_to_tf_key(name)[:-len(_SUFFIX)] + "/.OPTIMIZER_SLOT/optimizer/" + slot + _SUFFIX
+
+
+def save_tf_checkpoint(prefix, state_dict, step=0, adam_m=None, adam_v=None, opt_step=None):
+    """Write the model weights under the reference's object-graph keys, the ``step`` counter of train.py:246 and -- when
+    given -- the Adam moments (``{name: tensor}``, slots ``m`` / ``v``) and the optimizer's iteration count
+    (``optimizer/iter``), i.e. everything ``tf.train.Checkpoint(step=, optimizer=, model=)`` (train.py:246) persists, so a
+    resumed run continues with the right bias correction instead of restarting Adam at t = 1.  Scalars (``pos_weight``,
+    ``step``, ``iter``) are written with shape [] like TF does.  No object-graph proto is written (see module docstring)."""
+    tensors = {}
+    for k, v in state_dict.items():
+        a = np.asarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v, dtype=np.float32)
+        if k.endswith("pos_weight"):
+            a = a.reshape(())                       # tf.Variable(1.0): shape [] (encoder.py:64, posterior.py:95, transform.py:35)
+        tensors[name_to_tf_key(k)] = a
+    for slot, src in (("m", adam_m), ("v", adam_v)):
+        if src is None:
+            continue
+        for k, v in src.items():
+            a = np.asarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v, dtype=np.float32)
+            if k.endswith("pos_weight"):
+                a = a.reshape(())
+            tensors[_slot_key(k, slot)] = a
+    if opt_step is not None:
+        tensors["optimizer/iter" + _SUFFIX] = np.asarray(int(opt_step), dtype=np.int64)
     tensors["step" + _SUFFIX] = np.asarray(step, dtype=np.int64)
     write_bundle(prefix, tensors)
+
+
+def load_tf_optimizer_state(prefix):
+    """(adam_m, adam_v, iter) stored in the checkpoint ``prefix`` ({name: array} per slot; iter None when absent)."""
+    m, v, it = {}, {}, None
+    for key, a in read_bundle(prefix).items():
+        if key == "optimizer/iter" + _SUFFIX:
+            it = int(a)
+        elif "/.OPTIMIZER_SLOT/optimizer/" in key and key.endswith(_SUFFIX):
+            base, slot = key[:-len(_SUFFIX)].split("/.OPTIMIZER_SLOT/optimizer/")
+            name = tf_key_to_name(base + _SUFFIX)
+            if name is not None and slot in ("m", "v"):
+                (m if slot == "m" else v)[name] = a
+    return m, v, it
