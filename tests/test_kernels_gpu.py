@@ -92,7 +92,9 @@ def ref_attention(q, k, v, q_len, k_len, H, causal):
 
 
 @pytest.mark.parametrize("B,H,Tq,Tk,causal", [(2, 4, 128, 128, True), (3, 4, 435, 435, True), (3, 4, 435, 148, False),
-                                              (2, 2, 50, 300, False), (1, 4, 600, 600, True), (2, 4, 148, 148, False)])
+                                              (2, 2, 50, 300, False), (1, 4, 600, 600, True), (2, 4, 148, 148, False),
+                                              (2, 4, 448, 448, True), (3, 4, 100, 100, True), (2, 4, 320, 320, True),
+                                              (16, 4, 336, 336, True), (2, 4, 449, 449, True)])
 @pytest.mark.parametrize("want_ali", [False, True])
 def test_attention(B, H, Tq, Tk, causal, want_ali):
     """MultiHeadScaledProductAttention core incl. ragged lengths and fully masked (uniform) rows."""

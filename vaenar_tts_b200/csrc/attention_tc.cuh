@@ -753,4 +753,249 @@ attention2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
+
+// ================================================================================================ v3: scores resident in TMEM
+// Causal self-attention (query_lengths == key_lengths, the CrossAttentionBLK self-attention of attention.py:437-439) with
+// T <= 448: ONE tensor-core pass.  All key blocks of the tile are loaded once, every S_j = Q K_j^T is issued up front
+// into its own TMEM columns (4 x 128 score columns + 64 for O = 512) and stays there: the softmax warps sweep the
+// resident scores twice (row maximum, then p = exp2(...) -> fp16 P_j in shared memory -> O += P_j V_j) -- no second
+// Q K^T, no second sweep over K.  Only the diagonal block needs a mask (key <= query); fully masked rows (query >= length)
+// attend uniformly over all T keys as in the reference (attention.py:240-242) and take the column mean of V.
+// Tiles are scheduled heaviest first (blockIdx.y = 0 is the LAST query tile, which sees the most key blocks).
+constexpr int AT3_THREADS = 576;
+constexpr int AT3_MAXBLK = 4;
+constexpr int AT3_TMAX = 448;
+constexpr int AT3_OFF_K = ATT_QBYTES;
+constexpr int AT3_OFF_V = AT3_OFF_K + AT3_MAXBLK * ATT_KBYTES;
+constexpr int AT3_OFF_P = AT3_OFF_V + AT3_MAXBLK * ATT_VBYTES;
+constexpr int AT3_OFF_BARS = AT3_OFF_P + 2 * ATT_PBYTES;
+constexpr int AT3_SMEM = AT3_OFF_BARS + 256 + (2 * 4 * 128 + 64) * 4 + 1024;
+
+__global__ void __launch_bounds__(AT3_THREADS, 1)
+attention3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + AT3_OFF_K;
+  uint8_t* sV = smem + AT3_OFF_V;
+  uint8_t* sP = smem + AT3_OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT3_OFF_BARS);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [4]
+  uint64_t* v_full = bars + 5;    // [4]
+  uint64_t* s_full = bars + 9;    // [4]
+  uint64_t* p_full = bars + 13;   // [2]
+  uint64_t* p_empty = bars + 15;  // [2]
+  uint64_t* o_full = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  float* red = reinterpret_cast<float*>(bars + 32);   // [2][4][128]
+  float* vmean = red + 2 * 4 * 128;                   // [64]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nq = gridDim.y;
+  const int qt = nq - 1 - static_cast<int>(blockIdx.y);   // heaviest tiles first
+  const int q0 = qt * ATT_BQ;
+  const int h = blockIdx.x % p.H;
+  const int b = blockIdx.x / p.H;
+  const int len = __ldg(p.q_len + b);
+  const int q_hi = min(q0 + ATT_BQ, p.Tq);
+  const bool has_dead_rows = max(q0, len) < q_hi || len <= 0;
+  const bool all_dead = q0 >= len || len <= 0;
+  // key blocks that can contribute to the live rows: causal (keys <= last live query of the tile)
+  const int nblk = all_dead ? 0 : (min(q_hi, len) - 1) / ATT_BK + 1;
+  auto blk_n = [&](int j) -> int {   // score columns of block j (multiple of 16): zero-filled keys beyond T are masked causally
+    return min(ATT_BK, ((p.Tk - j * ATT_BK + 15) >> 4) << 4);
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < AT3_MAXBLK; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&p_full[i], 16);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmVt);
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const uint32_t tmem_O = tmem_base + AT3_TMAX;
+
+  if (warp == 0) {
+    // ===================== TMA producer: everything is resident, no ring =====================
+    if (nblk > 0 && elect_one()) {
+      mbar_arrive_expect_tx(q_full, ATT_QBYTES);
+      tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + h * ATT_D, q0, b);
+      for (int j = 0; j < nblk; ++j) {
+        mbar_arrive_expect_tx(&k_full[j], ATT_KBYTES);
+        tma_load_3d(sK + j * ATT_KBYTES, &tmK, &k_full[j], p.k_col0 + h * ATT_D, j * ATT_BK, b);
+      }
+      const long vrow = p.vt_row0 + (static_cast<long>(b) * p.H + h) * ATT_D;
+      for (int j = 0; j < nblk; ++j) {
+        const int npanel = blk_n(j) > 64 ? 2 : 1;
+        mbar_arrive_expect_tx(&v_full[j], npanel * (ATT_VBYTES / 2));
+        for (int q = 0; q < npanel; ++q)
+          tma_load_2d(sV + j * ATT_VBYTES + q * (ATT_VBYTES / 2), &tmVt, &v_full[j], j * ATT_BK + q * 64, static_cast<int>(vrow));
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (nblk > 0 && elect_one()) {
+      constexpr uint32_t idesc_o = umma_idesc_f16(ATT_BQ, ATT_D);
+      mbar_wait(q_full, 0);
+      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&k_full[j], 0);
+        tc_fence_after();
+        const uint32_t idesc_s = umma_idesc_f16(ATT_BQ, static_cast<uint32_t>(blk_n(j)));
+        const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + j * ATT_KBYTES));
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_f16(tmem_base + j * ATT_BK, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[j]);
+      }
+      for (int j = 0; j < nblk; ++j) {
+        const int sp = j & 1;
+        mbar_wait(&p_full[sp], (j >> 1) & 1);
+        mbar_wait(&v_full[j], 0);
+        tc_fence_after();
+        const int nsteps = blk_n(j) >> 4;
+        for (int kk = 0; kk < nsteps; ++kk) {
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sP + sp * ATT_PBYTES + (kk >> 2) * (ATT_PBYTES / 2))) + 2 * (kk & 3);
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sV + j * ATT_VBYTES + (kk >> 2) * (ATT_VBYTES / 2))) + 2 * (kk & 3);
+          umma_f16(tmem_O, adesc, bdesc, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&p_empty[sp]);
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // ===================== softmax / epilogue warps =====================
+    const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;             // 32 score columns of every 128-key block
+    const int r = quad * 32 + lane;
+    const int q = q0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const bool row_dead = (q >= len) || (len <= 0);
+    const bool row_store = q < p.Tq;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    uint32_t v[32];
+    auto softmax_bar = []() { asm volatile("bar.sync 1, 512;" ::: "memory"); };
+    auto warp_arrive = [&](uint64_t* bar) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    if (has_dead_rows) {
+      // column mean of V over ALL Tk keys (uniform attention of a fully masked row), 8 threads per head channel
+      const int sidx = (warp - 2) * 32 + lane;
+      const int d = sidx >> 3, part = sidx & 7;
+      const __half* vrow = p.vt + (p.vt_row0 + (static_cast<long>(b) * p.H + h) * ATT_D + d) * p.vt_ld;
+      float acc = 0.f;
+      for (int t = part; t < p.Tk; t += 8) acc += __half2float(vrow[t]);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (part == 0) vmean[d] = acc / static_cast<float>(p.Tk);
+    }
+    // ---- sweep 1: row maximum over the resident scores
+    float m = -INFINITY;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(&s_full[j], 0);
+      tc_fence_after();
+      if (grp * 32 < blk_n(j)) {
+        tmem_ld32(tmem_base + lane_off + j * ATT_BK + grp * 32, v);
+        tmem_wait_ld();
+        const int kk0 = j * ATT_BK + grp * 32;
+        if (kk0 + 31 <= q) {                       // whole chunk below the diagonal (warp-divergent only in the diagonal block)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) m = fmaxf(m, __uint_as_float(v[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) m = fmaxf(m, (kk0 + e <= q) ? __uint_as_float(v[e]) : -INFINITY);
+        }
+      }
+    }
+    red[grp * 128 + r] = m;
+    softmax_bar();
+    m = fmaxf(fmaxf(red[r], red[128 + r]), fmaxf(red[256 + r], red[384 + r]));
+    const float msl2 = row_dead ? INFINITY : m * sl2;   // live row: key 0 is always visible, m is finite
+    // ---- sweep 2: probabilities -> shared memory (A operand of P V)
+    float l = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      const int sp = j & 1;
+      if (j >= 2) mbar_wait(&p_empty[sp], ((j >> 1) - 1) & 1);
+      if (grp * 32 < blk_n(j)) {
+        tc_fence_after();
+        tmem_ld32(tmem_base + lane_off + j * ATT_BK + grp * 32, v);
+        tmem_wait_ld();
+        const int kk0 = j * ATT_BK + grp * 32;
+        float pr[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float pe = ex2_approx(fmaf(__uint_as_float(v[e]), sl2, -msl2));
+          if (kk0 + e > q) pe = 0.f;
+          l += pe;
+          pr[e] = pe;
+        }
+        uint8_t* prow = sP + sp * ATT_PBYTES + (grp >> 1) * (ATT_PBYTES / 2) + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_half2(pr[g * 8 + 0], pr[g * 8 + 1]);
+          u.y = pack_half2(pr[g * 8 + 2], pr[g * 8 + 3]);
+          u.z = pack_half2(pr[g * 8 + 4], pr[g * 8 + 5]);
+          u.w = pack_half2(pr[g * 8 + 6], pr[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(prow + ((((grp & 1) * 4 + g) ^ (r & 7)) << 4)) = u;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      warp_arrive(&p_full[sp]);
+    }
+    red[512 + grp * 128 + r] = l;
+    softmax_bar();
+    l = (red[512 + r] + red[640 + r]) + (red[768 + r] + red[896 + r]);
+    // ---- epilogue: ctx = O / l, 16 head channels per thread
+    if (nblk > 0) {
+      mbar_wait(o_full, 0);
+      tc_fence_after();
+      tmem_ld16(tmem_O + lane_off + grp * 16, v);
+      tmem_wait_ld();
+    }
+    if (row_store) {
+      const float on = row_dead ? 0.f : 1.0f / l;
+      float f[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) f[e] = row_dead ? vmean[grp * 16 + e] : __uint_as_float(v[e]) * on;
+      __half* dst = p.ctx + (static_cast<long>(b) * p.Tq + q) * p.ctx_ld + h * ATT_D + grp * 16;
+      uint4 ua, ub;
+      ua.x = pack_half2(f[0], f[1]); ua.y = pack_half2(f[2], f[3]); ua.z = pack_half2(f[4], f[5]); ua.w = pack_half2(f[6], f[7]);
+      ub.x = pack_half2(f[8], f[9]); ub.y = pack_half2(f[10], f[11]); ub.z = pack_half2(f[12], f[13]); ub.w = pack_half2(f[14], f[15]);
+      *reinterpret_cast<uint4*>(dst) = ua;
+      *reinterpret_cast<uint4*>(dst + 8) = ub;
+    }
+    tc_fence_before();
+  }
+  pdl_launch_dependents();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace vb

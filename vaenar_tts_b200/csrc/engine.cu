@@ -505,6 +505,9 @@ static void build_model(vaenar_model& m) {
     }
     plan_bw(m, "bw.dec.res", "decoder.residual_projection.kernel", h.post_filters, O);
   }
+  // folded flow maps as split-fp16 tensor-core operands (fused row-kernel tail): per step [hi: 128 x 128 | lo: 128 x 128], K-major
+  m.add_mat("flow.f", h.prior_n_blk * 2 * L, L);
+  m.add_mat("flow.b", h.prior_n_blk * 2 * L, L);
   // flow constants
   const int S = h.prior_n_blk;
   auto region = [&](int64_t bytes) {
@@ -649,6 +652,7 @@ static void set_attrs(vaenar_model* m) {
   VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attention2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attention2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
+  VB_CUDA(cudaFuncSetAttribute(attention3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_DKDV_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_DQ_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB2_DKDV_SMEM));
@@ -901,6 +905,22 @@ static void run_attention(Ctx& c, int B, int H, const AttnCall& a) {
   // chains), 64-key blocks / two CTAs per SM (more overlap when the grid is several waves deep: the B32 training step).
   // Measured: C2 inference 1.995 ms (v1) vs 2.022 ms (v2); C3 train step 14.30 ms (v1) vs 14.14 ms (v2).
   static const char* att_env = getenv("VAENAR_ATTN");
+  // v3: causal self-attention with the scores resident in TMEM (one tensor-core pass); forward-only shapes up to T = 448
+  if ((!att_env || att_env[0] == '3') && a.causal && a.q_len == a.k_len && a.Tq == a.Tk && a.Tk <= AT3_TMAX && !a.ali && !a.lse2) {
+    cfg.gridDim = dim3(H * B, cdiv(a.Tq, ATT_BQ));
+    cfg.blockDim = dim3(AT3_THREADS);
+    cfg.dynamicSmemBytes = AT3_SMEM;
+    cfg.stream = c.stream;
+    cudaLaunchAttribute attr3[1];
+    attr3[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr3[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+    cfg.attrs = attr3;
+    cfg.numAttrs = 1;
+    const cudaError_t le3 = cudaLaunchKernelEx(&cfg, attention3_tc_kernel, tQ, tK, tV, p);
+    if (le3 != cudaSuccess) VB_THROW("cudaLaunchKernelEx(attention3_tc_kernel) failed: %s", cudaGetErrorString(le3));
+    check_launch("attention3_tc_kernel");
+    return;
+  }
   const bool att_v1 = att_env ? att_env[0] == '1' : (grid.x * grid.y * grid.z <= 2u * 148u);
   cfg.blockDim = dim3(att_v1 ? ATT_THREADS : ATT2_THREADS);
   cfg.dynamicSmemBytes = att_v1 ? ATT_SMEM : ATT2_SMEM;
@@ -1096,9 +1116,23 @@ static XblkBufs xblk_bufs(Ctx& c, int B, int T, int d, int H, int ffn) {
 static bool xrow_supported(int d, int H, int ffn, int Tt, const MemKV& kv) {
   return g_use_fused && d == XR_D && H == XR_H && ffn == XR_F && kv.d == XR_D && Tt >= 1 && Tt <= XR_TK_MAX;
 }
+// What follows the last CrossAttentionBLK of a coupling net inside the same launch (csrc/xblk_fused.cuh, "flow tail")
+struct XTail {
+  bool coupling = false, flow = false, pre = false;
+  std::string out_pk;            // packed [log_scale | shift] projection ("prior.s.out") and its bias vector
+  float* z = nullptr;            // [rows, 128] flow state
+  int zp_off = 0;
+  bool backward = false;
+  float* row_acc = nullptr;
+  const __half* flow_w = nullptr;   // packed hi | lo map of the flow operation that follows
+  const float* flow_c = nullptr;
+  std::string pre_pk, pre_pn;    // next step's pre-projection ("prior.s.pre", "prior.glow.s.affine_coupling.net")
+  int cond_off_next = 0;
+  const float* pe = nullptr;
+};
 static void run_xblk_row(Ctx& c, const std::string& pk, const std::string& pn, const std::string& next_pk, Stream2 x,
                          const XblkBufs& b, int B, int T, const int* q_len, const MemKV& kv, int kv_blk, int Tt,
-                         const int* t_len, float* ali) {
+                         const int* t_len, float* ali, const XTail* tail = nullptr) {
   if (c.dry) return;
   const int d = XR_D, H = XR_H;
   XRowParams p;
@@ -1118,6 +1152,16 @@ static void run_xblk_row(Ctx& c, const std::string& pk, const std::string& pn, c
   p.has_next = next_pk.empty() ? 0 : 1;
   p.qk_next = b.qk; p.vt_next = b.vt; p.vt_next_ld = b.tpad;
   p.ali = ali;
+  if (tail && tail->coupling) {
+    if (tail->pre != !next_pk.empty()) VB_THROW("flow tail: the next q|k|v projection needs the next pre-projection and vice versa");
+    p.tail_coupling = 1; p.tail_flow = tail->flow ? 1 : 0; p.tail_pre = tail->pre ? 1 : 0;
+    p.z = tail->z; p.zp_off = tail->zp_off; p.cp_backward = tail->backward ? 1 : 0;
+    p.cp_bias = c.V(tail->out_pk + ".bias"); p.row_acc = tail->row_acc;
+    p.fl_c = tail->flow_c; p.cond_off_next = tail->cond_off_next;
+    if (tail->pre) {
+      p.pre_bias = c.P(tail->pre_pn + ".pre_projection.bias"); p.pre_pw = c.P(tail->pre_pn + ".pos_weight"); p.pe = tail->pe;
+    }
+  }
   if (g_xrow_dbg) {
     p.dbg = g_xrow_dbg;
     g_xrow_dbg += static_cast<size_t>(cdiv(T, 128)) * B * 128;
@@ -1134,8 +1178,12 @@ static void run_xblk_row(Ctx& c, const std::string& pk, const std::string& pn, c
   const CUtensorMap tF1 = make_tmap(c.W(pk + ".ffn1"), 2, d, XR_F, 1, d, 0, 64, 128);
   const CUtensorMap tF2 = make_tmap(c.W(pk + ".ffn2"), 2, XR_F, d, 1, XR_F, 0, 64, 128);
   const CUtensorMap tWn = p.has_next ? make_tmap(c.W(next_pk + ".qkv"), 2, d, 3 * d, 1, d, 0, 64, 128) : tWq;
+  const CUtensorMap tWo = p.tail_coupling ? make_tmap(c.W(tail->out_pk), 2, d, 128, 1, d, 0, 64, 128) : tWq;
+  const CUtensorMap tFl = p.tail_flow ? make_tmap(tail->flow_w, 2, 128, 256, 1, 128, 0, 64, 128) : tWq;
+  const CUtensorMap tWp = p.tail_pre ? make_tmap(c.W(tail->pre_pk), 2, 64, d, 1, 64, 0, 64, 128) : tWq;
   const double rows = static_cast<double>(B) * T;
-  const double macs_row = 2.0 * d * d + d * d + 2.0 * Tt * d + 2.0 * d * d + 2.0 * d * XR_F + (p.has_next ? 3.0 * d * d : 0.0);
+  const double macs_row = 2.0 * d * d + d * d + 2.0 * Tt * d + 2.0 * d * d + 2.0 * d * XR_F + (p.has_next ? 3.0 * d * d : 0.0) +
+                          (p.tail_coupling ? 128.0 * d : 0.0) + (p.tail_flow ? 128.0 * 128 : 0.0) + (p.tail_pre ? 64.0 * d : 0.0);
   const double wbytes = 2.0 * (4.0 * d * d + d * d + 2.0 * d * XR_F + (p.has_next ? 3.0 * d * d : 0.0));
   ProfileScope prof(ali ? "xblk_row_ali" : "xblk_row", 2.0 * rows * macs_row,
                     wbytes + rows * d * (4 + 2 + 2 + 4 + 2) + (p.has_next ? rows * 3 * d * 2 : 0) +
@@ -1152,7 +1200,7 @@ static void run_xblk_row(Ctx& c, const std::string& pk, const std::string& pn, c
   attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, xblk_row_kernel, tX, tA1, tK, tV, tW1, tWq, tW2, tF1, tF2, tWn, p);
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, xblk_row_kernel, tX, tA1, tK, tV, tW1, tWq, tW2, tF1, tF2, tWn, tWo, tFl, tWp, p);
   if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(xblk_row_kernel) failed: %s", cudaGetErrorString(le));
   check_launch("xblk_row_kernel");
 }
@@ -1162,7 +1210,7 @@ static void run_xblk_row(Ctx& c, const std::string& pk, const std::string& pn, c
 // the same about the block named by next_pk.
 static void xblk_fwd(Ctx& c, const std::string& pk, const std::string& pn, Stream2 x, const XblkBufs& b, int B, int T,
                      int d, int H, int ffn, const int* q_len, const MemKV& kv, int kv_blk, int Tt, const int* t_len,
-                     float* ali, const std::string& next_pk, bool& qkv_ready) {
+                     float* ali, const std::string& next_pk, bool& qkv_ready, const XTail* tail = nullptr) {
   const int rows = B * T;
   if (!qkv_ready) {  // self-attention projections: Q | K row-major, V transposed
     GemmParams p = gp();
@@ -1175,7 +1223,7 @@ static void xblk_fwd(Ctx& c, const std::string& pk, const std::string& pn, Strea
   run_attention(c, B, H, AttnCall{b.qk, 2 * d, 0, T, b.qk, 2 * d, d, T, b.vt, static_cast<long>(B) * H * 64, b.tpad, 0,
                                   q_len, q_len, 1, b.ctx, d, nullptr});
   if (xrow_supported(d, H, ffn, Tt, kv)) {
-    run_xblk_row(c, pk, pn, next_pk, x, b, B, T, q_len, kv, kv_blk, Tt, t_len, ali);
+    run_xblk_row(c, pk, pn, next_pk, x, b, B, T, q_len, kv, kv_blk, Tt, t_len, ali, tail);
     qkv_ready = !next_pk.empty();
     return;
   }
@@ -1222,12 +1270,18 @@ static void xblk_fwd(Ctx& c, const std::string& pk, const std::string& pn, Strea
 // all blocks of one module in sequence (the fused row kernel of block i also projects q|k|v of block i+1)
 static void xblk_stack_fwd(Ctx& c, const std::string& pk_prefix, const std::string& pn_prefix, int nblk, Stream2 x,
                            const XblkBufs& b, int B, int T, int d, int H, int ffn, const int* q_len, const MemKV& kv,
-                           int kv_blk0, int Tt, const int* t_len, float* ali, int64_t ali_blk_stride) {
-  bool qkv_ready = false;
-  for (int i = 0; i < nblk; ++i)
+                           int kv_blk0, int Tt, const int* t_len, float* ali, int64_t ali_blk_stride,
+                           bool* qkv_ready_io = nullptr, const XTail* tail = nullptr, const std::string& after_pk = std::string()) {
+  // qkv_ready_io: in = q|k|v of block 0 already projected (by the previous step's flow tail); out = the same about the block
+  // named by after_pk (the first block of the NEXT coupling net), which the flow tail of the last block projects
+  bool qkv_ready = qkv_ready_io ? *qkv_ready_io : false;
+  for (int i = 0; i < nblk; ++i) {
+    const bool last = i + 1 == nblk;
     xblk_fwd(c, pk_prefix + std::to_string(i), pn_prefix + std::to_string(i), x, b, B, T, d, H, ffn, q_len, kv, kv_blk0 + i,
              Tt, t_len, ali ? ali + static_cast<int64_t>(i) * ali_blk_stride : nullptr,
-             i + 1 < nblk ? pk_prefix + std::to_string(i + 1) : std::string(), qkv_ready);
+             last ? after_pk : pk_prefix + std::to_string(i + 1), qkv_ready, last ? tail : nullptr);
+  }
+  if (qkv_ready_io) *qkv_ready_io = qkv_ready;
 }
 
 // Conv1D wrapper of the reference: conv -> activation -> BatchNorm -> dropout (modules/utils.py:56-85).
@@ -1358,9 +1412,26 @@ static void length_predictor_fwd(Ctx& c, const float* text_embd, const int* t_le
   check_launch("length_predictor");
 }
 
-// One flow step's conditioner + coupling (modules/flow.py:223-257, modules/transform.py:45-59)
+// One flow step's conditioner + coupling (modules/flow.py:223-257, modules/transform.py:45-59).
+// `fuse`: what follows the coupling inside the fused row kernel of the step's last block (csrc/xblk_fused.cuh flow tail):
+//   flow_M / flow_c  the folded ActNorm (+) InvertibleLinear map applied to z right after the coupling (the NEXT flow
+//                    operation of the chain: step s+1 when sampling, step s itself when evaluating log p), or null;
+//   next_step        >= 0: also the pre-projection + positional encoding + first q|k|v projection of that step's net.
+// `pre_done`: x / q|k|v of this step were already produced by the previous step's tail.
+struct FlowFuse {
+  bool enabled = false;
+  const __half* flow_w = nullptr;
+  const float* flow_c = nullptr;
+  int next_step = -1;
+};
+static bool flow_tail_supported(Ctx& c, int Tt, const MemKV& kv) {
+  const vaenar_hparams_t& h = c.m->hp;
+  static const bool off = getenv("VAENAR_NO_FLOW_TAIL") != nullptr;
+  return !off && h.latent_dim == 128 && xrow_supported(h.prior_att_dim, h.prior_heads, h.prior_ffn, Tt, kv);
+}
 static void coupling_step(Ctx& c, int s, bool backward, float* z, __half* zh, float* row_acc, Stream2 x, const XblkBufs& xb,
-                          const float* pe, const MemKV& kv, int B, int Tz, int Tt, const int* z_len, const int* t_len) {
+                          const float* pe, const MemKV& kv, int B, int Tz, int Tt, const int* z_len, const int* t_len,
+                          bool pre_done = false, const FlowFuse& fuse = FlowFuse()) {
   const vaenar_hparams_t& h = c.m->hp;
   const int d = h.prior_att_dim, H = h.prior_heads, F = h.prior_ffn, L = h.latent_dim;
   const int rows = B * Tz;
@@ -1368,7 +1439,7 @@ static void coupling_step(Ctx& c, int s, bool backward, float* z, __half* zh, fl
   const int cond_off = upper ? 0 : L / 2;    // conditioning half
   const int zp_off = upper ? L / 2 : 0;      // transformed half
   const std::string pk = "prior." + std::to_string(s), pn = "prior.glow." + std::to_string(s) + ".affine_coupling.net";
-  {
+  if (!pre_done) {
     GemmParams p = gp();
     p.mode = EPI_PLAIN; p.N = d; segs_plain(p, L / 2);
     p.bias = c.P(pn + ".pre_projection.bias");
@@ -1376,8 +1447,30 @@ static void coupling_step(Ctx& c, int s, bool backward, float* z, __half* zh, fl
     p.out_f32 = x.f; p.ld_f32 = d; p.out_h = x.h; p.ld_h = d;
     run_gemm(c, 128, AOp{c.dry ? nullptr : zh + cond_off, L, L / 2}, AOp{}, 1, rows, c.W(pk + ".pre"), kpad64(L / 2), d, p);
   }
+  bool qkv_ready = pre_done;
+  if (fuse.enabled) {
+    XTail tail;
+    tail.coupling = true;
+    tail.out_pk = pk + ".out";
+    tail.z = z; tail.zp_off = zp_off; tail.backward = backward; tail.row_acc = row_acc;
+    tail.flow = fuse.flow_w != nullptr;
+    tail.flow_w = fuse.flow_w; tail.flow_c = fuse.flow_c;
+    std::string after;
+    if (fuse.next_step >= 0) {
+      const int ns = fuse.next_step;
+      tail.pre = true;
+      tail.pre_pk = "prior." + std::to_string(ns) + ".pre";
+      tail.pre_pn = "prior.glow." + std::to_string(ns) + ".affine_coupling.net";
+      tail.cond_off_next = (ns % 2 == 0) ? 0 : L / 2;
+      tail.pe = pe;
+      after = "prior." + std::to_string(ns) + ".blk0";
+    }
+    xblk_stack_fwd(c, pk + ".blk", pn + ".attentions.", h.prior_n_tblk, x, xb, B, Tz, d, H, F, z_len, kv, s * h.prior_n_tblk, Tt,
+                   t_len, nullptr, 0, &qkv_ready, &tail, after);
+    return;
+  }
   xblk_stack_fwd(c, pk + ".blk", pn + ".attentions.", h.prior_n_tblk, x, xb, B, Tz, d, H, F, z_len, kv, s * h.prior_n_tblk, Tt,
-                 t_len, nullptr, 0);
+                 t_len, nullptr, 0, &qkv_ready);
   {
     GemmParams p = gp();
     p.mode = EPI_COUPLING; p.N = L; segs_plain(p, d);
@@ -1387,7 +1480,6 @@ static void coupling_step(Ctx& c, int s, bool backward, float* z, __half* zh, fl
     p.row_acc = row_acc; p.lengths = z_len;
     run_gemm(c, 128, AOp{x.h, d, d}, AOp{}, 1, rows, c.W(pk + ".out"), d, L, p);
   }
-  (void)cond_off;
 }
 
 static void flow_linear(Ctx& c, float* z, __half* zh, const float* M, const float* cvec, int64_t rows) {
@@ -1441,10 +1533,21 @@ static void prior_sample(Ctx& c, const float* text_embd, const int* t_len, const
   }
   const float* Mf = c.dry ? nullptr : reinterpret_cast<const float*>(c.packed + c.m->off_Mf);
   const float* cf = c.dry ? nullptr : reinterpret_cast<const float*>(c.packed + c.m->off_cf);
+  const bool fused = flow_tail_supported(c, Tt, b.kv);
+  const __half* Wf = c.dry ? nullptr : c.W("flow.f");
   for (int s = 0; s < h.prior_n_blk; ++s) {
-    flow_linear(c, z, b.zh, c.dry ? nullptr : Mf + static_cast<int64_t>(s) * L * L, c.dry ? nullptr : cf + s * L,
-                static_cast<int64_t>(B) * Tz);
-    coupling_step(c, s, false, z, b.zh, b.row_acc, b.x, b.xb, b.pe, b.kv, B, Tz, Tt, z_len, t_len);
+    const bool pre_done = fused && s > 0;    // the previous step's flow tail applied this step's map and pre-projection
+    if (!pre_done)
+      flow_linear(c, z, b.zh, c.dry ? nullptr : Mf + static_cast<int64_t>(s) * L * L, c.dry ? nullptr : cf + s * L,
+                  static_cast<int64_t>(B) * Tz);
+    FlowFuse fuse;
+    fuse.enabled = fused;
+    if (fused && s + 1 < h.prior_n_blk) {
+      fuse.flow_w = c.dry ? nullptr : Wf + static_cast<int64_t>(s + 1) * 2 * L * L;
+      fuse.flow_c = c.dry ? nullptr : cf + (s + 1) * L;
+      fuse.next_step = s + 1;
+    }
+    coupling_step(c, s, false, z, b.zh, b.row_acc, b.x, b.xb, b.pe, b.kv, B, Tz, Tt, z_len, t_len, pre_done, fuse);
   }
   if (!c.dry) {
     prior_logp_finalize_kernel<<<B, 256, 0, c.stream>>>(b.base, b.row_acc,
@@ -1495,9 +1598,19 @@ static void prior_logprob(Ctx& c, const float* z_in, const float* text_embd, con
   run_cast(c, z, b.zh, rows * L);
   const float* Mb = c.dry ? nullptr : reinterpret_cast<const float*>(c.packed + c.m->off_Mb);
   const float* cb = c.dry ? nullptr : reinterpret_cast<const float*>(c.packed + c.m->off_cb);
+  const bool fused = flow_tail_supported(c, Tt, b.kv);
+  const __half* Wb = c.dry ? nullptr : c.W("flow.b");
   for (int s = h.prior_n_blk - 1; s >= 0; --s) {
-    coupling_step(c, s, true, z, b.zh, b.row_acc, b.x, b.xb, b.pe, b.kv, B, Tz, Tt, z_len, t_len);
-    flow_linear(c, z, b.zh, c.dry ? nullptr : Mb + static_cast<int64_t>(s) * L * L, c.dry ? nullptr : cb + s * L, rows);
+    FlowFuse fuse;
+    fuse.enabled = fused;
+    if (fused) {   // the inverse map of THIS step follows its coupling; then the pre-projection of step s - 1
+      fuse.flow_w = c.dry ? nullptr : Wb + static_cast<int64_t>(s) * 2 * L * L;
+      fuse.flow_c = c.dry ? nullptr : cb + s * L;
+      fuse.next_step = s - 1;
+    }
+    coupling_step(c, s, true, z, b.zh, b.row_acc, b.x, b.xb, b.pe, b.kv, B, Tz, Tt, z_len, t_len,
+                  fused && s + 1 < h.prior_n_blk, fuse);
+    if (!fused) flow_linear(c, z, b.zh, c.dry ? nullptr : Mb + static_cast<int64_t>(s) * L * L, c.dry ? nullptr : cb + s * L, rows);
   }
   if (!c.dry) {
     VB_CUDA(cudaMemsetAsync(b.base, 0, B * sizeof(float), c.stream));
@@ -1868,6 +1981,13 @@ static void pack_weights(vaenar_model* m, const float* params, uint8_t* packed, 
                                               reinterpret_cast<float*>(packed + m->off_Mb),
                                               reinterpret_cast<float*>(packed + m->off_cb),
                                               reinterpret_cast<float*>(packed + m->off_consts));
+  {
+    const long n = static_cast<long>(S) * FLOW_DIM * FLOW_DIM;
+    flow_pack_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const float*>(packed + m->off_Mf), reinterpret_cast<__half*>(packed + m->pmats.at("flow.f").off), S);
+    flow_pack_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const float*>(packed + m->off_Mb), reinterpret_cast<__half*>(packed + m->pmats.at("flow.b").off), S);
+  }
   check_launch("flow prepare");
   VB_CUDA(cudaEventRecord(m->ev_flow_ready, stream));
   m->flow_pending = true;
@@ -2452,8 +2572,9 @@ int vaenar_test_attention(const float* q, const float* k, const float* v, const 
   VB_CUDA(cudaMemsetAsync(vt, 0xFF, static_cast<int64_t>(B) * D * tpad * 2, c.stream));   // NaN padding: must never leak
   vt_transpose_kernel<<<static_cast<unsigned>((nv + 255) / 256), 256, 0, c.stream>>>(v, vt, B, Tk, H, tpad);
   check_launch("vt_transpose");
-  run_attention(c, B, H, AttnCall{qh, D, 0, Tq, kh, D, 0, Tk, vt, static_cast<long>(B) * D, tpad, 0, q_len, k_len, causal, ch, D,
-                                  ali});
+  // causal self-attention masks keys with the query lengths (attention.py:437-439 passes the same tensor twice)
+  run_attention(c, B, H, AttnCall{qh, D, 0, Tq, kh, D, 0, Tk, vt, static_cast<long>(B) * D, tpad, 0, q_len,
+                                  (causal && Tq == Tk) ? q_len : k_len, causal, ch, D, ali});
   const long nc = static_cast<long>(B) * Tq * D;
   half_to_float_kernel<<<static_cast<unsigned>((nc + 255) / 256), 256, 0, c.stream>>>(ch, ctx, nc);
   check_launch("half_to_float");

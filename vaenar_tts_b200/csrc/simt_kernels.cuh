@@ -313,6 +313,20 @@ __global__ void flow_fold_kernel(const float* const* __restrict__ Ws, const floa
   }
 }
 
+// Folded flow maps M[s][k][n] (fp32, z M convention) -> split-fp16 UMMA B operands out[s][0:128][k] = hi(M[k][n]) (row n),
+// out[s][128:256][k] = lo(M[k][n]): hi + lo carries 22 bits, z (hi, lo) x M (hi, lo) minus the lo x lo term ~ fp32 accuracy.
+__global__ void flow_pack_f16_kernel(const float* __restrict__ M, __half* __restrict__ out, int S) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long>(S) * FLOW_DIM * FLOW_DIM) return;
+  const int s = static_cast<int>(i / (FLOW_DIM * FLOW_DIM));
+  const int k = static_cast<int>((i / FLOW_DIM) % FLOW_DIM), n = static_cast<int>(i % FLOW_DIM);
+  const float m = M[i];
+  const __half hi = __float2half_rn(m);
+  __half* o = out + static_cast<long>(s) * 2 * FLOW_DIM * FLOW_DIM;
+  o[static_cast<long>(n) * FLOW_DIM + k] = hi;
+  o[static_cast<long>(FLOW_DIM + n) * FLOW_DIM + k] = __float2half_rn(m - __half2float(hi));
+}
+
 // y[rows,128] = x[rows,128] M[128,128] + c  in fp32 (CUDA cores; exactness matters more than speed here:
 // the flow state z carries the log-density).  In place is safe: a CTA stages its 32 rows first.
 // Also emits the fp16 copy consumed by the conditioner's pre-projection GEMM.

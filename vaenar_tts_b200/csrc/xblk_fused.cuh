@@ -66,21 +66,38 @@ struct XRowParams {
   const float* vec[XR_NVEC];
   const float* bf1;      // [1024] ffn dense1 bias
   float* x_f;            // [B*T, 256] fp32 residual stream (in / out)
-  int has_next;          // also project q|k|v of the next block
+  int has_next;          // tail bit 0: also project q|k|v of the next block (of this module, or of the next flow step's net)
   __half* qk_next;       // [B*T, 512] Q | K row-major
   __half* vt_next;       // [B*H*64, vt_next_ld] V transposed
   int vt_next_ld;
+  // ---- flow tail of the LAST block of a coupling net (modules/flow.py:223-257, modules/prior.py:135-168): the block
+  // output never leaves the SM; the coupling update of z, the next ActNorm (+) InvertibleLinear map (split-fp16 on the tensor
+  // cores) and the next step's pre-projection + positional encoding run in the same kernel.
+  int tail_coupling;     // z[:, zp_off : zp_off + 64] <- affine coupling with (log_scale, shift) = x' W_out + b
+  int tail_flow;         // z <- z M + c  (M = folded 128 x 128 map of the NEXT flow operation)
+  int tail_pre;          // x <- z[:, cond_off_next : +64] W_pre + b + pos_weight * PE[t]  (input of the next coupling net)
+  float* z;              // [B*T, 128] fp32 flow state (in / out)
+  int zp_off;            // transformed half of this step
+  int cp_backward;       // 0: zp * scale + shift ; 1: (zp - shift) / (scale + 1e-12)
+  const float* cp_bias;  // [128] log_scale_proj bias | shift_proj bias
+  float* row_acc;        // [B*T] per-row log-det accumulator (+=)
+  const float* fl_c;     // [128] offset of the folded flow map
+  int cond_off_next;     // conditioning half of the next step
+  const float* pre_bias; // [256]
+  const float* pre_pw;   // [1] pos_weight of the next net
+  const float* pe;       // [T, 256] positional-encoding table
   float* ali;            // optional [B, H, T, Tt] fp32 cross-attention alignments
   unsigned long long* dbg;   // optional per-CTA phase timestamps (tuning aid), 128 x u64 per CTA (globaltimer ns)
 };
 
-__global__ void __launch_bounds__(XR_THREADS, 1)
+__global__ void __launch_bounds__(XR_THREADS, 1)   // 18 warps (allocated as 20): at most 96 registers per thread
 xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmVt,
                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmWq,
                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmF1,
                 const __grid_constant__ CUtensorMap tmF2, const __grid_constant__ CUtensorMap tmWn,
-                const __grid_constant__ XRowParams p) {
+                const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmFl,
+                const __grid_constant__ CUtensorMap tmWp, const __grid_constant__ XRowParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* act0 = smem;
@@ -102,6 +119,8 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint64_t* hid_ready = bars + 22;       // [2] chunk drained (+ hidden panel written) (epilogue -> MMA)
   uint64_t* s_read = bars + 24;          // S_h copied into registers (epilogue -> MMA), 4 phases
   uint64_t* gfull = bars + 32;           // [8] per tile group, TMA -> MMA
+  uint64_t* t_full = bars + 40;          // [3] flow tail: coupling / flow / pre accumulators complete (MMA -> epilogue)
+  uint64_t* t_ready = bars + 43;         // [2] flow tail: z (hi | lo) panels / conditioning panel written (epilogue -> MMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
   float* lred = reinterpret_cast<float*>(smem + XR_OFF_RED);   // [2][4][128] LayerNorm row statistics
   float* sred = lred;                                          // [2][4][128] softmax row statistics (never live together)
@@ -140,12 +159,15 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_init(&hid_ready[0], XR_EPI_WARPS);
     mbar_init(&hid_ready[1], XR_EPI_WARPS);
     mbar_init(s_read, XR_EPI_WARPS);
+    for (int i = 0; i < 3; ++i) mbar_init(&t_full[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&t_ready[i], XR_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt);
     tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmWq); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmF1);
     tma_prefetch_desc(&tmF2); tma_prefetch_desc(&tmWn);
+    if (p.tail_coupling) { tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmFl); tma_prefetch_desc(&tmWp); }
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -252,6 +274,16 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (j + 2 < 8) fill_f1(j + 2);
       }
       stamp(102);
+      if (p.tail_coupling) {   // W_out [128 x 256]: two groups of two k-panels
+        group_w(&tmWo, 0, 0, 64, 0);
+        group_w(&tmWo, 128, 0, 192, 0);
+      }
+      if (p.tail_flow) {       // folded map, rows [0,128) = hi, [128,256) = lo: (hi x z_hi), (hi x z_lo), (lo x z_hi)
+        group_w(&tmFl, 0, 0, 64, 0);
+        group_w(&tmFl, 0, 0, 64, 0);
+        group_w(&tmFl, 0, 128, 64, 128);
+      }
+      if (p.tail_pre) group_w(&tmWp, 0, 0, 0, 128);   // W_pre [256 x 64]: the two column halves
       if (p.has_next)
         for (int j = 0; j < 6; ++j) {
           group_w(&tmWn, 0, j * 128, 64, j * 128);
@@ -387,9 +419,33 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       umma_commit(r_full);
       stamp(82);
+      // ---- 6a. flow tail: coupling projection, folded flow map (split-fp16), next pre-projection
+      uint32_t x_par = 0;   // parity of the act_ready phase that announces the A operand of the next stage
+      if (p.tail_coupling) {
+        mbar_wait(act_ready, x_par);
+        x_par ^= 1;
+        tc_fence_after();
+        mma_pair_k(a0, SCR, false);
+        mma_pair_k(a0 + 2 * XR_PANEL, SCR, true);
+        umma_commit(&t_full[0]);
+      }
+      if (p.tail_flow) {
+        mbar_wait(&t_ready[0], 0);   // z as fp16 hi (ACT1 panels 0, 1) and lo (panels 2, 3)
+        tc_fence_after();
+        mma_pair_k(a1, SCR + 128, false);                  // z_hi M_hi
+        mma_pair_k(a1 + 2 * XR_PANEL, SCR + 128, true);    // z_lo M_hi
+        mma_pair_k(a1, SCR + 128, true);                   // z_hi M_lo
+        umma_commit(&t_full[1]);
+      }
+      if (p.tail_pre) {
+        mbar_wait(&t_ready[1], 0);   // conditioning half of the new z in ACT1 panel 0
+        tc_fence_after();
+        mma_pair_n(a1, R, false);
+        umma_commit(&t_full[2]);
+      }
       // ---- 6. q|k|v of the next block: six 128-column chunks through the scratch buffers
       if (p.has_next) {
-        mbar_wait(act_ready, 0);
+        mbar_wait(act_ready, x_par);
         tc_fence_after();
         stamp(83);
         for (int j = 0; j < 6; ++j) {
@@ -488,7 +544,32 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
     // LayerNorm of R (+ bias) over the 256 columns; fp16 result -> ACT0 panel `grp`; fp32 result back into R, or
     // (final) to global memory.  vi = index of the bias vector in pvec (gamma, beta follow).
-    auto ln_epi = [&](int vi, bool final_out) {
+    // x' (fp16 panels in ACT0 already written + fenced by every thread) -> global by TMA store; x' (fp32, in xu) through the slab
+    auto store_x_global = [&](const uint32_t* xu) {
+      bar_all();   // all four panels written and fenced
+      if (st) {
+        for (int pn = 0; pn < 4; ++pn) tma_store_3d(&tmX, act0 + pn * XR_PANEL, pn * 64, t0, b);
+        tma_store_commit();
+      }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *sw(lane, g) = make_uint4(xu[hh * 32 + g * 4 + 0], xu[hh * 32 + g * 4 + 1], xu[hh * 32 + g * 4 + 2],
+                                    xu[hh * 32 + g * 4 + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + (lane >> 3), chunk = lane & 7;
+          if (row < rows_here)
+            *reinterpret_cast<uint4*>(p.x_f + (grow0 + row) * XR_D + grp * 64 + hh * 32 + chunk * 4) = *sw(row, chunk);
+        }
+      }
+    };
+    // out_mode 0: fp32 result back into R (residual of the next stage); 1: block output -> global; 2: block output stays on chip
+    auto ln_epi = [&](int vi, int out_mode) {
+      const bool final_out = out_mode != 0;
       const float* bias = pvec + vi * XR_D + grp * 64;
       const float* gamma = bias + XR_D;
       const float* beta = gamma + XR_D;
@@ -548,36 +629,14 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (vi == 3) estamp(117);
       tc_fence_before();
       warp_arrive(act_ready);
-      if (final_out) {
-        // x' (fp16) -> global with one TMA store per panel straight out of ACT0; x' (fp32) through the staging slab
-        bar_all();   // all four panels written and fenced
-        if (st) {
-          for (int pn = 0; pn < 4; ++pn) tma_store_3d(&tmX, act0 + pn * XR_PANEL, pn * 64, t0, b);
-          tma_store_commit();
-        }
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          __syncwarp();
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *sw(lane, g) = make_uint4(xu[hh * 32 + g * 4 + 0], xu[hh * 32 + g * 4 + 1], xu[hh * 32 + g * 4 + 2],
-                                      xu[hh * 32 + g * 4 + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int row = it * 4 + (lane >> 3), chunk = lane & 7;
-            if (row < rows_here)
-              *reinterpret_cast<uint4*>(p.x_f + (grow0 + row) * XR_D + grp * 64 + hh * 32 + chunk * 4) = *sw(row, chunk);
-          }
-        }
-      }
+      if (out_mode == 1) store_x_global(xu);
     };
 
     // ---- 1. s = LN1(R)
     mbar_wait(r_full, 0);
     tc_fence_after();
     estamp(2);
-    ln_epi(0, false);
+    ln_epi(0, 0);
     estamp(3);
 
     // ---- 2. cross-attention queries: scratch -> fp16 -> ACT1 panel (== head) `grp`
@@ -749,7 +808,7 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_wait(r_full, 1);
     tc_fence_after();
     estamp(22);
-    ln_epi(3, false);
+    ln_epi(3, 0);
     estamp(23);
 
     // ---- 5. FFN hidden chunks: relu(acc + b1) -> fp16 -> ACT1 buffer (j & 1), two panels of 64 hidden columns
@@ -785,9 +844,141 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_wait(r_full, 0);
     tc_fence_after();
     estamp(40);
-    ln_epi(6, true);
+    ln_epi(6, p.tail_coupling ? 2 : 1);
     estamp(41);
     pdl_launch_dependents();   // late trigger: a parked dependent grid would only block SMs the other launch chain needs
+
+    // ---- 6a. flow tail (last block of a coupling net)
+    if (p.tail_coupling) {
+      // affine coupling (modules/flow.py:223-257): thread (r, grp) owns 16 of the 64 transformed channels and, for the
+      // flow map that follows, the matching 16 channels of the conditioning half
+      const long grow = static_cast<long>(b) * p.T + t;
+      const int cond_off = 64 - p.zp_off;
+      float zp[16], zc[16];
+#pragma unroll
+      for (int e4 = 0; e4 < 4; ++e4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c4 = a;
+        if (row_ok) {
+          a = *reinterpret_cast<const float4*>(p.z + grow * 128 + p.zp_off + grp * 16 + e4 * 4);
+          if (p.tail_flow) c4 = *reinterpret_cast<const float4*>(p.z + grow * 128 + cond_off + grp * 16 + e4 * 4);
+        }
+        zp[e4 * 4 + 0] = a.x; zp[e4 * 4 + 1] = a.y; zp[e4 * 4 + 2] = a.z; zp[e4 * 4 + 3] = a.w;
+        zc[e4 * 4 + 0] = c4.x; zc[e4 * 4 + 1] = c4.y; zc[e4 * 4 + 2] = c4.z; zc[e4 * 4 + 3] = c4.w;
+      }
+      mbar_wait(&t_full[0], 0);
+      tc_fence_after();
+      uint32_t ls[16], sh[16];
+      tmem_ld16(SCR + grp * 16, ls);
+      tmem_ld16(SCR + 64 + grp * 16, sh);
+      tmem_wait_ld();
+      float logdet = 0.f;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float l_ = __uint_as_float(ls[e]) + __ldg(p.cp_bias + grp * 16 + e);
+        const float s_ = __uint_as_float(sh[e]) + __ldg(p.cp_bias + 64 + grp * 16 + e);
+        const float scale = __fdividef(1.f, 1.f + __expf(-(l_ + 2.0f)));   // sigmoid(log_scale + 2), flow.py:231
+        zp[e] = p.cp_backward ? __fdividef(zp[e] - s_, scale + 1e-12f) : scale * zp[e] + s_;
+        logdet += __logf(scale);
+      }
+      sred[grp * 128 + r] = logdet;
+      bar_all();
+      if (grp == 0 && row_ok) {
+        const float tot = (sred[r] + sred[128 + r]) + (sred[256 + r] + sred[384 + r]);
+        if (t < qlen) p.row_acc[grow] += p.cp_backward ? -tot : tot;
+      }
+      if (!p.tail_flow) {
+        if (row_ok) {
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4)
+            *reinterpret_cast<float4*>(p.z + grow * 128 + p.zp_off + grp * 16 + e4 * 4) =
+                make_float4(zp[e4 * 4 + 0], zp[e4 * 4 + 1], zp[e4 * 4 + 2], zp[e4 * 4 + 3]);
+        }
+      } else {
+        // the updated z row as split fp16 (hi | lo) A operands: z column c lives in panel (c >> 6) (hi) / 2 + (c >> 6) (lo)
+        auto put = [&](const float* vals, int col0) {   // 16 consecutive z columns starting at col0 (multiple of 16)
+          float lo[16];
+          uint4 h0, h1, l0, l1;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) lo[e] = vals[e] - __half2float(__float2half_rn(vals[e]));
+          h0.x = pack_half2(vals[0], vals[1]); h0.y = pack_half2(vals[2], vals[3]); h0.z = pack_half2(vals[4], vals[5]); h0.w = pack_half2(vals[6], vals[7]);
+          h1.x = pack_half2(vals[8], vals[9]); h1.y = pack_half2(vals[10], vals[11]); h1.z = pack_half2(vals[12], vals[13]); h1.w = pack_half2(vals[14], vals[15]);
+          l0.x = pack_half2(lo[0], lo[1]); l0.y = pack_half2(lo[2], lo[3]); l0.z = pack_half2(lo[4], lo[5]); l0.w = pack_half2(lo[6], lo[7]);
+          l1.x = pack_half2(lo[8], lo[9]); l1.y = pack_half2(lo[10], lo[11]); l1.z = pack_half2(lo[12], lo[13]); l1.w = pack_half2(lo[14], lo[15]);
+          const int pn = col0 >> 6, ch = (col0 & 63) >> 3;
+          uint8_t* hrow = act1 + pn * XR_PANEL + r * 128;
+          uint8_t* lrow = act1 + (2 + pn) * XR_PANEL + r * 128;
+          *reinterpret_cast<uint4*>(hrow + ((ch ^ (r & 7)) << 4)) = h0;
+          *reinterpret_cast<uint4*>(hrow + (((ch + 1) ^ (r & 7)) << 4)) = h1;
+          *reinterpret_cast<uint4*>(lrow + ((ch ^ (r & 7)) << 4)) = l0;
+          *reinterpret_cast<uint4*>(lrow + (((ch + 1) ^ (r & 7)) << 4)) = l1;
+        };
+        put(zp, p.zp_off + grp * 16);
+        put(zc, cond_off + grp * 16);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        warp_arrive(&t_ready[0]);
+        // z <- z M + c: 32 of the 128 columns per thread
+        mbar_wait(&t_full[1], 0);
+        tc_fence_after();
+        tmem_ld32(SCR + 128 + grp * 32, v);
+        tmem_wait_ld();
+        float z2[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) z2[e] = __uint_as_float(v[e]) + __ldg(p.fl_c + grp * 32 + e);
+        if (row_ok) {
+#pragma unroll
+          for (int e4 = 0; e4 < 8; ++e4)
+            *reinterpret_cast<float4*>(p.z + grow * 128 + grp * 32 + e4 * 4) =
+                make_float4(z2[e4 * 4 + 0], z2[e4 * 4 + 1], z2[e4 * 4 + 2], z2[e4 * 4 + 3]);
+        }
+        if (p.tail_pre) {
+          // conditioning half of the next step -> fp16 A operand (ACT1 panel 0; the flow MMAs that read ACT1 are complete)
+          const int c0 = grp * 32 - p.cond_off_next;
+          if (c0 >= 0 && c0 < 64) {
+            uint8_t* crow = act1 + r * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 u;
+              u.x = pack_half2(z2[g * 8 + 0], z2[g * 8 + 1]); u.y = pack_half2(z2[g * 8 + 2], z2[g * 8 + 3]);
+              u.z = pack_half2(z2[g * 8 + 4], z2[g * 8 + 5]); u.w = pack_half2(z2[g * 8 + 6], z2[g * 8 + 7]);
+              *reinterpret_cast<uint4*>(crow + ((((c0 >> 3) + g) ^ (r & 7)) << 4)) = u;
+            }
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          warp_arrive(&t_ready[1]);
+          // x <- cond W_pre + b + pos_weight * PE[t]  (modules/transform.py:47-52): the input of the next coupling net
+          mbar_wait(&t_full[2], 0);
+          tc_fence_after();
+          float xs[64];
+          uint32_t* xu = reinterpret_cast<uint32_t*>(xs);
+          tmem_ld32(R + grp * 64, xu);
+          tmem_ld32(R + grp * 64 + 32, xu + 32);
+          tmem_wait_ld();
+          const float pw = __ldg(p.pre_pw);
+          const float* perow = p.pe + static_cast<long>(min(t, p.T - 1)) * XR_D + grp * 64;
+#pragma unroll
+          for (int g = 0; g < 16; ++g) {
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(p.pre_bias + grp * 64 + g * 4));
+            const float4 pq = __ldg(reinterpret_cast<const float4*>(perow + g * 4));
+            xs[g * 4 + 0] += bq.x + pw * pq.x; xs[g * 4 + 1] += bq.y + pw * pq.y;
+            xs[g * 4 + 2] += bq.z + pw * pq.z; xs[g * 4 + 3] += bq.w + pw * pq.w;
+          }
+          uint8_t* prow = act0 + grp * XR_PANEL + r * 128;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            uint4 u;
+            u.x = pack_half2(xs[g * 8 + 0], xs[g * 8 + 1]); u.y = pack_half2(xs[g * 8 + 2], xs[g * 8 + 3]);
+            u.z = pack_half2(xs[g * 8 + 4], xs[g * 8 + 5]); u.w = pack_half2(xs[g * 8 + 6], xs[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(prow + ((g ^ (r & 7)) << 4)) = u;
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          warp_arrive(act_ready);
+          store_x_global(xu);
+        }
+      }
+    }
 
     // ---- 7. next block's q | k (row-major) and v (transposed)
     if (p.has_next) {
