@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "vaenar_tts_b200", "libvaenar_sm100.so")
 ROUND = sys.argv[1] if len(sys.argv) > 1 else "r1"
-MN = ["UTCHMMA", "LDTM", "UTMALDG", "UTCBAR", "UTCATOMSWS", "REDG", "ATOMG", "SYNCS", "BAR.SYNC", "HMMA", "FFMA", "DFMA", "MUFU"]
+MN = ["UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "UTCATOMSWS", "REDG", "ATOMG", "SYNCS", "BAR.SYNC", "HMMA", "FFMA", "DFMA", "MUFU"]
 
 
 def demangle(names):

@@ -976,6 +976,8 @@ attention3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tmem_ld16(tmem_O + lane_off + grp * 16, v);
       tmem_wait_ld();
     }
+    if (p.lse2 && grp == 0 && row_store)   // training: log2 of the softmax denominator incl. the maximum (backward pass)
+      p.lse2[(static_cast<long>(b) * p.H + h) * p.Tq + q] = row_dead ? 0.f : msl2 + log2f(l);
     if (row_store) {
       const float on = row_dead ? 0.f : 1.0f / l;
       float f[16];

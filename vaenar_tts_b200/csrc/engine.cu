@@ -905,8 +905,8 @@ static void run_attention(Ctx& c, int B, int H, const AttnCall& a) {
   // chains), 64-key blocks / two CTAs per SM (more overlap when the grid is several waves deep: the B32 training step).
   // Measured: C2 inference 1.995 ms (v1) vs 2.022 ms (v2); C3 train step 14.30 ms (v1) vs 14.14 ms (v2).
   static const char* att_env = getenv("VAENAR_ATTN");
-  // v3: causal self-attention with the scores resident in TMEM (one tensor-core pass); forward-only shapes up to T = 448
-  if ((!att_env || att_env[0] == '3') && a.causal && a.q_len == a.k_len && a.Tq == a.Tk && a.Tk <= AT3_TMAX && !a.ali && !a.lse2) {
+  // v3: causal self-attention with the scores resident in TMEM (one tensor-core pass), T <= 448; also the training forward
+  if ((!att_env || att_env[0] == '3') && a.causal && a.q_len == a.k_len && a.Tq == a.Tk && a.Tk <= AT3_TMAX && !a.ali) {
     cfg.gridDim = dim3(H * B, cdiv(a.Tq, ATT_BQ));
     cfg.blockDim = dim3(AT3_THREADS);
     cfg.dynamicSmemBytes = AT3_SMEM;

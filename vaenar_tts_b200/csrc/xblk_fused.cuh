@@ -245,9 +245,9 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (int pn = 0; pn < 4; ++pn) tma_load_3d(act1 + pn * XR_PANEL, &tmA1, a1_full, pn * 64, t0, b);
       for (int kp = 2; kp < 8; ++kp) group_w(&tmW1, kp * 64, 0, kp * 64, 128);
       stamp(98);
-      // att_proj2, s half, then the cross-attention query projection
-      for (int kp = 0; kp < 4; ++kp) group_w(&tmW2, kp * 64, 0, kp * 64, 128);
+      // the cross-attention query projection, then att_proj2's s half (its MMAs run while the epilogue converts q)
       for (int kp = 0; kp < 4; ++kp) group_w(&tmWq, kp * 64, 0, kp * 64, 128);
+      for (int kp = 0; kp < 4; ++kp) group_w(&tmW2, kp * 64, 0, kp * 64, 128);
       stamp(99);
       // cross attention: K_0, then per head K_{h+1}, V_h (S_{h+1} is issued before P_h V_h)
       group_k(0);
@@ -342,13 +342,13 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (int kp = 0; kp < 4; ++kp) mma_pair_n(a1 + kp * XR_PANEL, R, true);
       umma_commit(r_full);
       stamp(67);
-      // ---- 2. R (= s) += s Wp2[:256] ; scratch = s Wcq
+      // ---- 2. scratch = s Wcq ; R (= s) += s Wp2[:256]
       mbar_wait(act_ready, 0);
       tc_fence_after();
       stamp(68);
-      for (int kp = 0; kp < 4; ++kp) mma_pair_n(a0 + kp * XR_PANEL, R, true);
       for (int kp = 0; kp < 4; ++kp) mma_pair_n(a0 + kp * XR_PANEL, SCR, kp > 0);
       umma_commit(sc_full);
+      for (int kp = 0; kp < 4; ++kp) mma_pair_n(a0 + kp * XR_PANEL, R, true);
       stamp(69);
       // ---- 3. cross attention, S_h = Q_h K_h^T into scratch [0, TKP), O_h = P_h V_h into scratch [192, 256)
       auto mma_s = [&](int h) {
