@@ -104,7 +104,7 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint8_t* act1 = smem + XR_ACT;
   uint8_t* ring = smem + XR_OFF_RING;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + XR_OFF_BARS);
-  uint64_t* empty = bars;                // [5] per ring slot, MMA -> TMA
+  uint64_t* empty = bars + 48;           // [5] per ring slot: free again (MMA -> TMA); every completion is waited exactly once
   uint64_t* a_full = bars + 10;          // x (fp16) panels landed in ACT0
   uint64_t* a1_full = bars + 11;         // self-attention context panels landed in ACT1
   uint64_t* r_init = bars + 12;          // residual stored into R (epilogue -> MMA)
@@ -142,8 +142,8 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < XR_NSLOT; ++i) mbar_init(&empty[i], 1);
     for (int i = 0; i < XR_NGRP; ++i) mbar_init(&gfull[i], 1);
+    for (int i = 0; i < XR_NSLOT; ++i) mbar_init(&empty[i], 1);
     mbar_init(a_full, 1);
     mbar_init(a1_full, 1);
     mbar_init(r_init, XR_EPI_WARPS);
@@ -186,24 +186,18 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // =========================================================== TMA producer
     // The ring streams 16 KB tiles; consecutive tiles form GROUPS (two weight tiles, or the K / V^T tiles of one head)
     // that share one "full" barrier, so that the MMA issuer pays one barrier wait (~180 cycles) per 32 KB instead of
-    // per tile.  Slots are released per tile; the producer learns about two releases from one wait.
+    // per tile.  Slots are released per tile (one commit each); the producer waits for every release exactly once.
     if (elect_one()) {
       int f = 0;           // tile index (slot = f % XR_NSLOT)
-      int g = 0;           // group index (barrier = g % XR_NGRP)
-      int known = -1;      // highest tile index known to be consumed
+      int g = 0;           // group index (full barrier = g % XR_NGRP)
       uint64_t* gbar = nullptr;
       auto begin_group = [&](uint32_t bytes) {
         gbar = &gfull[g & (XR_NGRP - 1)];
         mbar_arrive_expect_tx(gbar, bytes);
         ++g;
       };
-      auto acquire = [&]() -> uint8_t* {
-        const int need = f - XR_NSLOT;     // the tile that used this slot before
-        if (need > known) {
-          const int w = min(need + 1, f - 1);   // in-order consumption: waiting for a later tile covers the earlier one
-          mbar_wait(&empty[w % XR_NSLOT], (w / XR_NSLOT) & 1);
-          known = w;
-        }
+      auto acquire = [&]() -> uint8_t* {   // slots are released per tile; the previous use of this slot is use (f / NSLOT) - 1
+        if (f >= XR_NSLOT) mbar_wait(&empty[f % XR_NSLOT], ((f / XR_NSLOT) - 1) & 1);
         return ring + (f % XR_NSLOT) * XR_SLOT;
       };
       // two weight tiles [128 out-rows x 64 k] at (k0, n0) and (k1, n1)
@@ -588,6 +582,7 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         q4[0] = fmaf(x0, x0, q4[0]); q4[1] = fmaf(x1, x1, q4[1]); q4[2] = fmaf(x2, x2, q4[2]); q4[3] = fmaf(x3, x3, q4[3]);
         xs[g * 4 + 0] = x0; xs[g * 4 + 1] = x1; xs[g * 4 + 2] = x2; xs[g * 4 + 3] = x3;
       }
+      bar_all();   // the statistics scratch is shared with the softmax (ordering would otherwise only follow from the mbarrier chain)
       lred[grp * 128 + r] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       lred[512 + grp * 128 + r] = (q4[0] + q4[1]) + (q4[2] + q4[3]);
       if (vi == 3) estamp(111);
@@ -793,6 +788,7 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         warp_arrive(o_done);
         estamp(9 + 4 * h);
       };
+      bar_all();   // LayerNorm statistics scratch -> softmax statistics scratch
       float il = sm_compute(0);
       write_p(0, il);
       for (int h = 0; h < XR_H; ++h) {
@@ -880,6 +876,7 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         zp[e] = p.cp_backward ? __fdividef(zp[e] - s_, scale + 1e-12f) : scale * zp[e] + s_;
         logdet += __logf(scale);
       }
+      bar_all();
       sred[grp * 128 + r] = logdet;
       bar_all();
       if (grp == 0 && row_ok) {
@@ -920,6 +917,7 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         // z <- z M + c: 32 of the 128 columns per thread
         mbar_wait(&t_full[1], 0);
         tc_fence_after();
+        bar_all();   // explicit edge: every thread's (hi | lo) panel writes precede the re-use of ACT1 panel 0 below
         tmem_ld32(SCR + 128 + grp * 32, v);
         tmem_wait_ld();
         float z2[32];
