@@ -264,6 +264,31 @@ int vaenar_test_attention_bwd(const float* q, const float* k, const float* v, co
                               const int32_t* k_len, int B, int H, int Tq, int Tk, int causal, float* dq, float* dk,
                               float* dv, void* ws, int64_t ws_bytes, void* stream);
 
+/* ---- mel inversion downstream of the path (csrc/griffin_lim.cuh) ----
+ * Replaces audio/audio.py:81-84 (Audio.inv_mel_spectrogram) as called per utterance by
+ * audio/utils.py:24-40 (TestUtils.synthesize_and_save_wavs), batched over utterances.  n_fft is fixed at 2048
+ * (num_freq 1025, configs/hparams.py:268,386); n_frames[b] = mel length of utterance b (>= 2); the waveform of
+ * utterance b has hop_length * (n_frames[b] - 1) samples (librosa.istft, center=True). */
+int64_t vaenar_griffin_lim_workspace_bytes(int B, int T, int win_length, int hop_length);
+/* audio.py:157-165,180-182,196-206: S = max(1e-10, pinv(mel_basis) @ db_to_amp(denormalize(mel) + ref_level_db)) ** power
+ * in the reference's float32 arithmetic.  mel [B,T,n_mels] fp32 (normalised, as the decoder emits it); inv_basis_t
+ * [n_mels,num_freq] fp32 = pinv(mel_basis) transposed; S [B,T,num_freq] fp64 (the reference's complex128 magnitudes). */
+int vaenar_mel_to_linear(const float* mel, const int32_t* n_frames, const float* inv_basis_t, int B, int T, int n_mels,
+                         int num_freq, float min_level_db, float ref_level_db, float max_abs_value, int symmetric,
+                         float power, double* S, void* stream);
+/* audio.py:93-102 (Audio._griffin_lim) with librosa 0.8.0 stft/istft semantics (audio.py:104-143): `iters` projections
+ * after the random-phase start.  rand [B,T,num_freq] fp64 = the np.random.rand draw (NULL: Philox stream from `seed`).
+ * wav [B, wav_ld] fp64, zero beyond each utterance's length. */
+int vaenar_griffin_lim(const double* S, const int32_t* n_frames, const double* rand, uint64_t seed, int B, int T,
+                       int num_freq, int win_length, int hop_length, int iters, void* ws, int64_t ws_bytes, double* wav,
+                       int64_t wav_ld, void* stream);
+/* audio.py:224-226 (Audio.inv_preemphasize): y[n] = x[n] + k y[n-1] in place (scipy.signal.lfilter([1], [1, -k], x)). */
+int vaenar_inv_preemphasis(double* wav, int64_t wav_ld, const int32_t* n_frames, int B, int T, int win_length,
+                           int hop_length, double k, void* ws, int64_t ws_bytes, void* stream);
+/* audio.py:18-21 (Audio.save_wav up to the file): out = int16(wav * 32767 / max(0.01, max |wav|)) per utterance. */
+int vaenar_wav_to_int16(const double* wav, int64_t wav_ld, const int32_t* n_frames, int B, int T, int win_length,
+                        int hop_length, void* ws, int64_t ws_bytes, int16_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

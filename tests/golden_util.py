@@ -49,3 +49,13 @@ def train_masks(hps, g, prefix="train"):
     sites += [f"dec.postnet.{i}" for i in range(hps.Decoder.post_n_conv)]
     assert len(sites) == n, (len(sites), n)
     return dict(zip(sites, ms))
+
+
+def speechlike_mel(rng, T, n_mels=80):
+    """Smooth normalised mel in [0, 1] with silence at both ends (float32, as the decoder emits it): the synthetic
+    input of the mel-inversion tests (tests/golden/make_golden_audio.py, tests/test_audio_gpu.py)."""
+    tt = np.arange(T)[:, None] / max(T - 1, 1)
+    m = np.arange(n_mels)[None, :] / n_mels
+    env = np.sin(np.pi * tt) ** 0.5
+    mel = 0.55 * env * (1 - 0.6 * m) + 0.15 * np.sin(2 * np.pi * (3 * tt + 2 * m)) * env + 0.05 * rng.standard_normal((T, n_mels))
+    return np.clip(mel, 0, 1).astype(np.float32)

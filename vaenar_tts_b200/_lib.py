@@ -91,6 +91,13 @@ _SIGS = {
     "vaenar_xblk_stack_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "vaenar_set_fused": (c_int, [c_int]),
     "vaenar_debug_xrow_timestamps": (c_int, [_P]),
+    "vaenar_griffin_lim_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "vaenar_mel_to_linear": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_float, _P,
+                                     _P]),
+    "vaenar_griffin_lim": (c_int, [_P, _P, _P, c_uint64, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P, c_int64,
+                                   _P]),
+    "vaenar_inv_preemphasis": (c_int, [_P, c_int64, _P, c_int, c_int, c_int, c_int, ctypes.c_double, _P, c_int64, _P]),
+    "vaenar_wav_to_int16": (c_int, [_P, c_int64, _P, c_int, c_int, c_int, c_int, _P, c_int64, _P, _P]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -38,15 +38,32 @@ ln_bwd_kernel(const float* dy, const float* __restrict__ y, const float* __restr
 #pragma unroll
     for (int e = 0; e < 4; ++e) ag[j][e] = ab[j][e] = au[j][e] = 0.f;
   const long r0 = static_cast<long>(blockIdx.x) * 32;
-  for (int rr = warp; rr < 32; rr += 8) {
-    const long row = r0 + rr;
+  // a warp owns rows warp, warp + 8, warp + 16, warp + 24 of the tile: all their loads are issued before the first store
+  // (du may alias dy, which keeps the compiler from overlapping the rows itself)
+  float4 dvs[4][NJ], yvs[4][NJ];
+  float rss[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long row = r0 + warp + 8 * u;
+    if (row < rows) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        dvs[u][j] = *reinterpret_cast<const float4*>(dy + row * D + (j * 32 + lane) * 4);
+        yvs[u][j] = *reinterpret_cast<const float4*>(y + row * D + (j * 32 + lane) * 4);
+      }
+      rss[u] = rstd[row];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long row = r0 + warp + 8 * u;
     if (row >= rows) break;
     float d[NJ][4], xh[NJ][4];
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const float4 dv = *reinterpret_cast<const float4*>(dy + row * D + (j * 32 + lane) * 4);
-      const float4 yv = *reinterpret_cast<const float4*>(y + row * D + (j * 32 + lane) * 4);
+      const float4 dv = dvs[u][j];
+      const float4 yv = yvs[u][j];
       const float dd[4] = {dv.x, dv.y, dv.z, dv.w}, yy[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -63,7 +80,7 @@ ln_bwd_kernel(const float* dy, const float* __restrict__ y, const float* __restr
     }
     c1 = warp_sum(c1) * (1.0f / D);
     c2 = warp_sum(c2) * (1.0f / D);
-    const float rs = rstd[row];
+    const float rs = rss[u];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       float o[4];
@@ -74,10 +91,10 @@ ln_bwd_kernel(const float* dy, const float* __restrict__ y, const float* __restr
       }
       *reinterpret_cast<float4*>(du + row * D + (j * 32 + lane) * 4) = make_float4(o[0], o[1], o[2], o[3]);
       if (du_h) {
-        uint2 u;
-        u.x = pack_half2(o[0], o[1]);
-        u.y = pack_half2(o[2], o[3]);
-        *reinterpret_cast<uint2*>(du_h + row * D + (j * 32 + lane) * 4) = u;
+        uint2 u2;
+        u2.x = pack_half2(o[0], o[1]);
+        u2.y = pack_half2(o[2], o[3]);
+        *reinterpret_cast<uint2*>(du_h + row * D + (j * 32 + lane) * 4) = u2;
       }
     }
   }
@@ -138,35 +155,49 @@ __device__ __forceinline__ void st8h(__half* p, const float* v) {
 
 // ------------------------------------------------------------------ activation / dropout backward + bias gradient
 // out_h = g * mask * [act > 0]   (mask nullable: inverted-dropout keep mask; act: post-ReLU (and post-dropout) activation),
-// dbias[c] += column sums.  64 rows per CTA, 8 columns per thread; C % 8 == 0, C <= 2048.  out_h may alias g (TG == __half).
+// dbias[c] += column sums.  RELU_ROWS rows per CTA, 8 columns per thread; C % 8 == 0, C <= 2048.  out_h may alias g
+// (TG == __half), so the loads of four row steps are issued before the first store (memory-level parallelism: the
+// compiler cannot hoist loads over possibly aliasing stores itself).
+constexpr int RELU_ROWS = 32;
 template <typename TG>
 __global__ void __launch_bounds__(256)
 relu_bwd_kernel(const TG* g, const float* __restrict__ mask, const __half* __restrict__ act, long rows, int C,
                 __half* out_h, float* __restrict__ dbias) {
   __shared__ float red[256 * 8];
   const ColLayout<8> L(C);
-  const long r0 = static_cast<long>(blockIdx.x) * 64;
-  const long r1 = min(rows, r0 + 64);
+  const long r0 = static_cast<long>(blockIdx.x) * RELU_ROWS;
+  const long r1 = min(rows, r0 + RELU_ROWS);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (L.active)
-    for (long r = r0 + L.lane; r < r1; r += L.lanes) {
-      const long i = r * C + L.g * 8;
-      float v[8], a[8];
-      ld8(g + i, v);
-      if (mask) {
-        float m[8];
-        ld8(mask + i, m);
+    for (long rb = r0 + L.lane; rb < r1; rb += 4L * L.lanes) {
+      float v[4][8], a[4][8], m[4][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] *= m[e];
+      for (int u = 0; u < 4; ++u) {
+        const long r = rb + static_cast<long>(u) * L.lanes;
+        if (r < r1) {
+          const long i = r * C + L.g * 8;
+          ld8(g + i, v[u]);
+          if (mask) ld8(mask + i, m[u]);
+          if (act) ld8(act + i, a[u]);
+        }
       }
-      if (act) {
-        ld8(act + i, a);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = a[e] > 0.f ? v[e] : 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const long r = rb + static_cast<long>(u) * L.lanes;
+        if (r < r1) {
+          if (mask) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[u][e] *= m[u][e];
+          }
+          if (act) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[u][e] = a[u][e] > 0.f ? v[u][e] : 0.f;
+          }
+          st8h(out_h + r * C + L.g * 8, v[u]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += v[u][e];
+        }
       }
-      st8h(out_h + i, v);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] += v[e];
     }
   if (dbias) {
     __syncthreads();

@@ -22,6 +22,7 @@
 #include "wgrad_tc.cuh"
 #include "xblk_fused.cuh"
 #include "bwd_kernels.cuh"
+#include "griffin_lim.cuh"
 
 using namespace vb;
 
@@ -662,7 +663,7 @@ static void set_attrs(vaenar_model* m) {
   VB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
   VB_CUDA(cudaFuncSetAttribute(slogdet128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOW_DIM * (FLOW_DIM + 1) * 8));
   VB_CUDA(cudaFuncSetAttribute(inverse128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FLOW_DIM * (2 * FLOW_DIM + 1) + FLOW_DIM) * 4));
-  VB_CUDA(cudaFuncSetAttribute(flow_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FLOW_DIM * FLOW_DIM + 32 * FLOW_DIM) * 4));
+  VB_CUDA(cudaFuncSetAttribute(flow_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOW_LIN_SMEM));
   done = true;
   (void)m;
 }
@@ -1484,7 +1485,7 @@ static void coupling_step(Ctx& c, int s, bool backward, float* z, __half* zh, fl
 
 static void flow_linear(Ctx& c, float* z, __half* zh, const float* M, const float* cvec, int64_t rows) {
   if (c.dry) return;
-  flow_linear_kernel<<<static_cast<unsigned>((rows + 31) / 32), 256, (FLOW_DIM * FLOW_DIM + 32 * FLOW_DIM) * 4, c.stream>>>(
+  flow_linear_kernel<<<static_cast<unsigned>((rows + FLOW_ROWS - 1) / FLOW_ROWS), 256, FLOW_LIN_SMEM, c.stream>>>(
       z, z, zh, M, cvec, rows, 0);
   check_launch("flow_linear");
 }
@@ -1918,10 +1919,10 @@ static void pack_weights(vaenar_model* m, const float* params, uint8_t* packed, 
   const int nops = static_cast<int>(m->host_ops.size());
   m->host_tiles.assign(nops + 1, 0);
   for (int i = 0; i < nops; ++i)
-    m->host_tiles[i + 1] = m->host_tiles[i] + cdiv(m->host_ops[i].N, 32) * cdiv(m->host_ops[i].K, 32);
+    m->host_tiles[i + 1] = m->host_tiles[i] + cdiv(m->host_ops[i].N, PACK_TILE) * cdiv(m->host_ops[i].K, PACK_TILE);
   int* dtiles = reinterpret_cast<int*>(packed + m->off_packtiles);
   VB_CUDA(cudaMemcpyAsync(dtiles, m->host_tiles.data(), (nops + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
-  pack_weights_flat_kernel<<<m->host_tiles[nops], dim3(32, 8), 0, stream>>>(dops, dtiles, nops);
+  pack_weights_flat_kernel<<<m->host_tiles[nops], 256, 0, stream>>>(dops, dtiles, nops);
   check_launch("pack_weights");
   (void)maxK; (void)maxN;
   auto PP = [&](const std::string& n) { return params + m->params[m->P(n)].offset; };
@@ -2291,9 +2292,13 @@ int vaenar_adam_step(float* params, const float* grads, float* m, float* v, cons
                      void* stream) {
   API_BEGIN
   if (step < 1) VB_THROW("Adam step counts from 1");
+  for (const void* q : {static_cast<const void*>(params), static_cast<const void*>(grads), static_cast<const void*>(m),
+                        static_cast<const void*>(v)})
+    if (reinterpret_cast<uintptr_t>(q) & 15) VB_THROW("adam_step: buffers must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(trainable_mask) & 3) VB_THROW("adam_step: trainable mask must be 4-byte aligned");
   const double lr_t = static_cast<double>(lr) * std::sqrt(1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(step))) /
                       (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(step)));
-  adam_step_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  adam_step_kernel<<<static_cast<unsigned>(((n + 3) / 4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       params, grads, m, v, trainable_mask, n, static_cast<float>(lr_t), beta1, beta2, eps, grad_scale, skip_flag);
   check_launch("adam_step");
   API_END
@@ -2397,6 +2402,138 @@ int vaenar_randn(float* out, int64_t n, uint64_t seed, uint64_t stream_id, float
   randn_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, seed,
                                                                                                     stream_id, stddev);
   check_launch("randn");
+  API_END
+}
+
+// ---------------------------------------------------------------------------- mel inversion (csrc/griffin_lim.cuh)
+struct GLWorkspace {
+  double2* tw;
+  double* window;
+  double* carry;
+  double* peak;
+  double* frames[2];
+  int max_chunks;
+};
+static int64_t gl_workspace_layout(int B, int T, int win, int hop, uint8_t* base, GLWorkspace* w) {
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    uint8_t* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const int64_t L = static_cast<int64_t>(hop) * std::max(T - 1, 0);
+  const int max_chunks = static_cast<int>((L + PRE_CHUNK - 1) / PRE_CHUNK) + 1;
+  uint8_t* tw = take(sizeof(double2) * (GL_N / 2));
+  uint8_t* window = take(sizeof(double) * GL_MAX_WIN);
+  uint8_t* carry = take(sizeof(double) * static_cast<int64_t>(B) * max_chunks);
+  uint8_t* peak = take(sizeof(double) * B);
+  uint8_t* f0 = take(sizeof(double) * static_cast<int64_t>(B) * T * win);
+  uint8_t* f1 = take(sizeof(double) * static_cast<int64_t>(B) * T * win);
+  if (w) {
+    w->tw = reinterpret_cast<double2*>(tw); w->window = reinterpret_cast<double*>(window);
+    w->carry = reinterpret_cast<double*>(carry); w->peak = reinterpret_cast<double*>(peak);
+    w->frames[0] = reinterpret_cast<double*>(f0); w->frames[1] = reinterpret_cast<double*>(f1);
+    w->max_chunks = max_chunks;
+  }
+  return off;
+}
+static void gl_check_shape(int B, int T, int num_freq, int win, int hop) {
+  if (num_freq != GL_BINS) VB_THROW("griffin_lim: num_freq %d unsupported (n_fft is fixed at %d, num_freq %d)", num_freq, GL_N, GL_BINS);
+  if (B < 1 || T < 2) VB_THROW("griffin_lim: need B >= 1 and at least 2 frames (B %d, T %d)", B, T);
+  if (win < 1 || win > GL_MAX_WIN || hop < 1 || hop > win) VB_THROW("griffin_lim: win_length %d / hop_length %d unsupported", win, hop);
+}
+static void gl_need_device() {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) VB_THROW("no CUDA device: the B200 path has no CPU fallback");
+}
+
+int64_t vaenar_griffin_lim_workspace_bytes(int B, int T, int win_length, int hop_length) {
+  if (B < 1 || T < 1 || win_length < 1 || hop_length < 1) return -1;
+  return gl_workspace_layout(B, T, win_length, hop_length, nullptr, nullptr);
+}
+
+int vaenar_mel_to_linear(const float* mel, const int32_t* n_frames, const float* inv_basis_t, int B, int T, int n_mels,
+                         int num_freq, float min_level_db, float ref_level_db, float max_abs_value, int symmetric,
+                         float power, double* S, void* stream) {
+  API_BEGIN
+  gl_need_device();
+  if (num_freq != GL_BINS) VB_THROW("mel_to_linear: num_freq %d unsupported (%d)", num_freq, GL_BINS);
+  if (n_mels < 1 || n_mels > 128) VB_THROW("mel_to_linear: num_mels %d unsupported (1..128)", n_mels);
+  if (B < 1 || T < 1) VB_THROW("mel_to_linear: empty batch");
+  MelToLinearParams p;
+  p.mel = mel; p.inv_t = inv_basis_t; p.n_frames = n_frames; p.S = S;
+  p.T = T; p.n_mels = n_mels; p.s_ld = GL_BINS; p.symmetric = symmetric;
+  p.min_level_db = min_level_db; p.ref_level_db = ref_level_db; p.max_abs = max_abs_value; p.power = power;
+  mel_to_linear_kernel<<<dim3(T, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  check_launch("mel_to_linear_kernel");
+  API_END
+}
+
+int vaenar_griffin_lim(const double* S, const int32_t* n_frames, const double* rand, uint64_t seed, int B, int T,
+                       int num_freq, int win_length, int hop_length, int iters, void* ws, int64_t ws_bytes, double* wav,
+                       int64_t wav_ld, void* stream) {
+  API_BEGIN
+  gl_need_device();
+  gl_check_shape(B, T, num_freq, win_length, hop_length);
+  if (iters < 0) VB_THROW("griffin_lim: iters %d", iters);
+  const int64_t L = static_cast<int64_t>(hop_length) * (T - 1);
+  if (wav_ld < L) VB_THROW("griffin_lim: wav row pitch %lld < %lld samples", (long long)wav_ld, (long long)L);
+  GLWorkspace w;
+  const int64_t need = gl_workspace_layout(B, T, win_length, hop_length, static_cast<uint8_t*>(ws), &w);
+  if (!ws || ws_bytes < need) VB_THROW("griffin_lim: workspace %lld < %lld bytes", (long long)ws_bytes, (long long)need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool attr_set = false;
+  const int smem = sizeof(double2) * (GL_ZSIZE + GL_N / 2);
+  if (!attr_set) {
+    VB_CUDA(cudaFuncSetAttribute(gl_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  gl_tables_kernel<<<cdiv(GL_N / 2, 256), 256, 0, st>>>(w.tw, w.window, win_length);
+  check_launch("gl_tables_kernel");
+  GLParams p;
+  memset(&p, 0, sizeof(p));
+  p.S = S; p.rand = rand; p.n_frames = n_frames; p.tw = w.tw; p.window = w.window; p.seed = seed;
+  p.T = T; p.s_ld = GL_BINS; p.win = win_length; p.hop = hop_length; p.lpad = (GL_N - win_length) / 2;
+  const dim3 grid(cdiv(T, 2), B);
+  for (int it = 0; it <= iters; ++it) {   // pass 0: y = istft(S * random phases); passes 1..iters: audio.py:98-100
+    p.first = it == 0;
+    p.prev = w.frames[(it + 1) & 1];
+    p.next = w.frames[it & 1];
+    gl_iter_kernel<<<grid, GL_THREADS, smem, st>>>(p);
+    check_launch("gl_iter_kernel");
+  }
+  gl_finalize_kernel<<<dim3(static_cast<unsigned>((wav_ld + 255) / 256), B), 256, 0, st>>>(
+      w.frames[iters & 1], w.window, n_frames, T, win_length, hop_length, p.lpad, wav, wav_ld);
+  check_launch("gl_finalize_kernel");
+  API_END
+}
+
+int vaenar_inv_preemphasis(double* wav, int64_t wav_ld, const int32_t* n_frames, int B, int T, int win_length,
+                           int hop_length, double k, void* ws, int64_t ws_bytes, void* stream) {
+  API_BEGIN
+  gl_need_device();
+  GLWorkspace w;
+  const int64_t need = gl_workspace_layout(B, T, win_length, hop_length, static_cast<uint8_t*>(ws), &w);
+  if (!ws || ws_bytes < need) VB_THROW("inv_preemphasis: workspace %lld < %lld bytes", (long long)ws_bytes, (long long)need);
+  inv_preemphasis_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(wav, wav_ld, n_frames, hop_length, k, w.carry,
+                                                                            w.max_chunks);
+  check_launch("inv_preemphasis_kernel");
+  API_END
+}
+
+int vaenar_wav_to_int16(const double* wav, int64_t wav_ld, const int32_t* n_frames, int B, int T, int win_length,
+                        int hop_length, void* ws, int64_t ws_bytes, int16_t* out, void* stream) {
+  API_BEGIN
+  gl_need_device();
+  GLWorkspace w;
+  const int64_t need = gl_workspace_layout(B, T, win_length, hop_length, static_cast<uint8_t*>(ws), &w);
+  if (!ws || ws_bytes < need) VB_THROW("wav_to_int16: workspace %lld < %lld bytes", (long long)ws_bytes, (long long)need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  wav_peak_kernel<<<B, 256, 0, st>>>(wav, wav_ld, n_frames, hop_length, w.peak);
+  check_launch("wav_peak_kernel");
+  wav_to_int16_kernel<<<dim3(static_cast<unsigned>((wav_ld + 255) / 256), B), 256, 0, st>>>(wav, wav_ld, n_frames, hop_length,
+                                                                                             w.peak, out);
+  check_launch("wav_to_int16_kernel");
   API_END
 }
 

@@ -45,8 +45,11 @@ __global__ void pack_weights_kernel(const PackOp* __restrict__ ops) {
   }
 }
 
-// Same, one CTA per 32x32 tile of the whole plan: tile_start[op] = first CTA of op (prefix sums, nops + 1 entries)
-__global__ void pack_weights_flat_kernel(const PackOp* __restrict__ ops, const int* __restrict__ tile_start, int nops) {
+// Same, one CTA (256 threads) per 64x64 tile of the whole plan: tile_start[op] = first CTA of op (prefix sums, nops + 1
+// entries).  Reads are float4 along N, writes half2 along K (mode 0/1) or along N (mode 2).
+constexpr int PACK_TILE = 64;
+__global__ void __launch_bounds__(256)
+pack_weights_flat_kernel(const PackOp* __restrict__ ops, const int* __restrict__ tile_start, int nops) {
   int lo = 0, hi = nops - 1;
   const int b = blockIdx.x;
   while (lo < hi) {
@@ -55,25 +58,26 @@ __global__ void pack_weights_flat_kernel(const PackOp* __restrict__ ops, const i
   }
   const PackOp op = ops[lo];
   const int t = b - tile_start[lo];
-  const int tn = (op.N + 31) / 32;
-  const int n0 = (t % tn) * 32, k0 = (t / tn) * 32;
-  __shared__ float tile[32][33];
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int k = k0 + i, n = n0 + threadIdx.x;
-    tile[i][threadIdx.x] = (k < op.K && n < op.N) ? op.src[static_cast<long>(k) * op.lds + n] : 0.f;
+  const int tn = (op.N + PACK_TILE - 1) / PACK_TILE;
+  const int n0 = (t % tn) * PACK_TILE, k0 = (t / tn) * PACK_TILE;
+  __shared__ float tile[PACK_TILE][PACK_TILE + 1];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4
+  for (int i = ty; i < PACK_TILE; i += 4) {
+    const int k = k0 + i, n = n0 + tx;
+    tile[i][tx] = (k < op.K && n < op.N) ? op.src[static_cast<long>(k) * op.lds + n] : 0.f;
   }
   __syncthreads();
   if (op.mode == 2) {
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-      const int k = k0 + i, n = n0 + threadIdx.x;
-      if (k < op.K && n < op.N) op.dst[static_cast<long>(k) * op.ldd + n] = __float2half_rn(tile[i][threadIdx.x]);
+    for (int i = ty; i < PACK_TILE; i += 4) {
+      const int k = k0 + i, n = n0 + tx;
+      if (k < op.K && n < op.N) op.dst[static_cast<long>(k) * op.ldd + n] = __float2half_rn(tile[i][tx]);
     }
     return;
   }
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int n = n0 + i, k = k0 + threadIdx.x;
+  for (int i = ty; i < PACK_TILE; i += 4) {
+    const int n = n0 + i, k = k0 + tx;
     if (n < op.N && k < op.K) {
-      const float v = tile[threadIdx.x][i];
+      const float v = tile[tx][i];
       const __half hi16 = __float2half_rn(v);
       op.dst[static_cast<long>(n) * op.ldd + k] = op.mode ? __float2half_rn(v - __half2float(hi16)) : hi16;
     }
@@ -328,57 +332,68 @@ __global__ void flow_pack_f16_kernel(const float* __restrict__ M, __half* __rest
 }
 
 // y[rows,128] = x[rows,128] M[128,128] + c  in fp32 (CUDA cores; exactness matters more than speed here:
-// the flow state z carries the log-density).  In place is safe: a CTA stages its 32 rows first.
+// the flow state z carries the log-density).  In place is safe: a CTA stages its 64 rows first.
 // Also emits the fp16 copy consumed by the conditioner's pre-projection GEMM.
+// Thread (ty, tx) owns rows ty*8..+7 and columns tx, tx+32, tx+64, tx+96; the k loop runs in ascending order with one
+// fmaf per term (the summation order every parity fixture was generated with).  transpose != 0 (backward pass:
+// g_in = g_out M^T) keeps M row-major in shared memory with a row pitch of 129 floats so that the column reads are
+// conflict-free.
+constexpr int FLOW_ROWS = 64;
+constexpr int FLOW_LIN_SMEM = (FLOW_DIM * (FLOW_DIM + 1) + FLOW_ROWS * FLOW_DIM) * 4;
 __global__ void __launch_bounds__(256)
 flow_linear_kernel(const float* z_in, float* z, __half* __restrict__ z_h, const float* __restrict__ M,
                    const float* __restrict__ c, long rows, int transpose) {
   extern __shared__ float smf[];
-  float* Ms = smf;                         // [128][128]
-  float* Xs = smf + FLOW_DIM * FLOW_DIM;   // [32][128]
-  const long r0 = static_cast<long>(blockIdx.x) * 32;
-  if (transpose) {   // backward pass: g_in = g_out M^T
-    for (int i = threadIdx.x; i < FLOW_DIM * FLOW_DIM; i += 256) Ms[(i % FLOW_DIM) * FLOW_DIM + i / FLOW_DIM] = M[i];
+  float* Ms = smf;                               // [128][128] or [128][129]
+  float* Xs = smf + FLOW_DIM * (FLOW_DIM + 1);   // [64][128]
+  const long r0 = static_cast<long>(blockIdx.x) * FLOW_ROWS;
+  if (transpose) {
+    for (int i = threadIdx.x; i < FLOW_DIM * FLOW_DIM; i += 256) Ms[(i / FLOW_DIM) * (FLOW_DIM + 1) + (i % FLOW_DIM)] = M[i];
   } else {
     for (int i = threadIdx.x; i < FLOW_DIM * FLOW_DIM / 4; i += 256)
       reinterpret_cast<float4*>(Ms)[i] = reinterpret_cast<const float4*>(M)[i];
   }
-  for (int i = threadIdx.x; i < 32 * FLOW_DIM / 4; i += 256) {
+  for (int i = threadIdx.x; i < FLOW_ROWS * FLOW_DIM / 4; i += 256) {
     const long row = r0 + (i * 4) / FLOW_DIM;
     reinterpret_cast<float4*>(Xs)[i] =
         row < rows ? reinterpret_cast<const float4*>(z_in + r0 * FLOW_DIM)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
-  const int tx = threadIdx.x & 31;   // columns tx*4 .. +3
-  const int ty = threadIdx.x >> 5;   // rows ty*4 .. +3
-  float acc[4][4];
+  const int tx = threadIdx.x & 31;
+  const int ty = threadIdx.x >> 5;
+  float acc[8][4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  const int ks = transpose ? 1 : FLOW_DIM;             // stride of k
+  const int ns = transpose ? (FLOW_DIM + 1) * 32 : 32; // stride of the thread's 4 columns
+  const float* mp = Ms + (transpose ? tx * (FLOW_DIM + 1) : tx);
+  const float* xp = Xs + ty * 8 * FLOW_DIM;
+#pragma unroll 4
   for (int k = 0; k < FLOW_DIM; ++k) {
-    const float4 m = *reinterpret_cast<const float4*>(Ms + k * FLOW_DIM + tx * 4);
+    const float m0 = mp[k * ks], m1 = mp[k * ks + ns], m2 = mp[k * ks + 2 * ns], m3 = mp[k * ks + 3 * ns];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const float x = Xs[(ty * 4 + a) * FLOW_DIM + k];
-      acc[a][0] = fmaf(x, m.x, acc[a][0]);
-      acc[a][1] = fmaf(x, m.y, acc[a][1]);
-      acc[a][2] = fmaf(x, m.z, acc[a][2]);
-      acc[a][3] = fmaf(x, m.w, acc[a][3]);
+    for (int a = 0; a < 8; ++a) {
+      const float x = xp[a * FLOW_DIM + k];
+      acc[a][0] = fmaf(x, m0, acc[a][0]);
+      acc[a][1] = fmaf(x, m1, acc[a][1]);
+      acc[a][2] = fmaf(x, m2, acc[a][2]);
+      acc[a][3] = fmaf(x, m3, acc[a][3]);
     }
   }
-  const float4 cc = c ? *reinterpret_cast<const float4*>(c + tx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float cc[4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const long row = r0 + ty * 4 + a;
+  for (int b = 0; b < 4; ++b) cc[b] = c ? c[tx + 32 * b] : 0.f;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const long row = r0 + ty * 8 + a;
     if (row < rows) {
-      const float4 o = make_float4(acc[a][0] + cc.x, acc[a][1] + cc.y, acc[a][2] + cc.z, acc[a][3] + cc.w);
-      *reinterpret_cast<float4*>(z + row * FLOW_DIM + tx * 4) = o;
-      if (z_h) {
-        uint2 u;
-        u.x = pack_half2(o.x, o.y);
-        u.y = pack_half2(o.z, o.w);
-        *reinterpret_cast<uint2*>(z_h + row * FLOW_DIM + tx * 4) = u;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const float o = acc[a][b] + cc[b];
+        z[row * FLOW_DIM + tx + 32 * b] = o;
+        if (z_h) z_h[row * FLOW_DIM + tx + 32 * b] = __float2half_rn(o);
       }
     }
   }
@@ -618,18 +633,46 @@ __global__ void nonfinite_count_kernel(const float* __restrict__ g, long n, floa
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(count, static_cast<float>(bad));
 }
 
-__global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                 float* __restrict__ v, const uint8_t* __restrict__ trainable, long n, float lr_t, float b1,
-                                 float b2, float eps, float grad_scale, const float* __restrict__ skip_flag) {
+__global__ void __launch_bounds__(256)
+adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 const uint8_t* __restrict__ trainable, long n, float lr_t, float b1, float b2, float eps, float grad_scale,
+                 const float* __restrict__ skip_flag) {
   if (skip_flag && *skip_flag != 0.f) return;   // non-finite gradients somewhere in the job: leave p, m, v untouched
-  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n || !trainable[i]) return;
-  const float gi = g[i] * grad_scale;
-  const float mi = b1 * m[i] + (1.f - b1) * gi;
-  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-  m[i] = mi;
-  v[i] = vi;
-  p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  const long j = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long i = j * 4;
+  if (i >= n) return;
+  if (i + 3 < n) {                              // four elements per thread (the flat buffers are 16-byte aligned)
+    const uchar4 tm = *reinterpret_cast<const uchar4*>(trainable + i);
+    if (!(tm.x | tm.y | tm.z | tm.w)) return;
+    const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+    float4 p4 = *reinterpret_cast<const float4*>(p + i), m4 = *reinterpret_cast<const float4*>(m + i),
+           v4 = *reinterpret_cast<const float4*>(v + i);
+    float* pe = &p4.x; float* me = &m4.x; float* ve = &v4.x; const float* ge = &g4.x;
+    const unsigned char te[4] = {tm.x, tm.y, tm.z, tm.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (!te[e]) continue;
+      const float gi = ge[e] * grad_scale;
+      const float mi = b1 * me[e] + (1.f - b1) * gi;
+      const float vi = b2 * ve[e] + (1.f - b2) * gi * gi;
+      me[e] = mi;
+      ve[e] = vi;
+      pe[e] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+    *reinterpret_cast<float4*>(m + i) = m4;
+    *reinterpret_cast<float4*>(v + i) = v4;
+    *reinterpret_cast<float4*>(p + i) = p4;
+    return;
+  }
+  for (long e = i; e < n; ++e) {
+    if (!trainable[e]) continue;
+    const float gi = g[e] * grad_scale;
+    const float mi = b1 * m[e] + (1.f - b1) * gi;
+    const float vi = b2 * v[e] + (1.f - b2) * gi * gi;
+    m[e] = mi;
+    v[e] = vi;
+    p[e] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
 }
 
 // Data-parallel optimiser step fused with the gradient exchange over NVLink peer memory (one process per GPU, buffers

@@ -20,8 +20,22 @@ class LJHPS:
         reduction_factors = [5, 4, 3, 2]
         reduce_interval = [0, 200, 400, 600]
 
-    class Audio:
+    class Audio:                      # configs/hparams.py:266-282; consumed by vaenar_tts_b200.audio (mel inversion)
         num_mels = 80
+        num_freq = 1025
+        min_mel_freq = 0.
+        max_mel_freq = 8000.
+        sample_rate = 22050
+        frame_length_sample = 1024
+        frame_shift_sample = 256
+        preemphasize = 0.97
+        min_level_db = -100.0
+        ref_level_db = 20.0
+        max_abs_value = 1
+        symmetric_specs = False
+        griffin_lim_iters = 60
+        power = 1.5
+        center = True
 
     class Common:
         latent_dim = 128
@@ -83,6 +97,12 @@ class LJHPS:
 class DataBakerHPS(LJHPS):
     class Train(LJHPS.Train):
         random_seed = 12
+
+    class Audio(LJHPS.Audio):         # configs/hparams.py:384-400
+        sample_rate = 16000
+        frame_length_sample = 800
+        frame_shift_sample = 200
+        min_level_db = -115.
 
     class Common(LJHPS.Common):
         mel_text_len_ratio = 4.21
