@@ -129,6 +129,8 @@ struct vaenar_model {
   std::vector<const float*> host_ptrs;
   std::vector<float*> host_gptrs;   // flow parameter-gradient pointers (train step)
   cudaStream_t wgrad_stream = nullptr;   // weight gradients run beside the activation-gradient chain (train step)
+  cudaStream_t lane_stream = nullptr;    // train step: decoder forward + backward run beside the prior's (both hang off z only)
+  cudaStream_t lane_wgrad_stream = nullptr;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_cursor = 0;
   bool attrs_set = false;
@@ -548,6 +550,8 @@ struct Ctx {
   uint64_t seed = 0;
   int update_bn = 1;
   cudaStream_t wstream = nullptr;        // when set, run_wgrad launches here after an event recorded on `stream`
+  cudaStream_t lane = nullptr;           // train step: stream of the decoder branch (null: everything on `stream`)
+  cudaStream_t lane_w = nullptr;         // weight-gradient stream of the decoder branch
 
   template <typename T>
   T* alloc(int64_t count) {
@@ -2051,6 +2055,8 @@ int vaenar_destroy(vaenar_handle_t h) {
     if (h->ev_flow_ready) cudaEventDestroy(h->ev_flow_ready);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->wgrad_stream) cudaStreamDestroy(h->wgrad_stream);
+    if (h->lane_stream) cudaStreamDestroy(h->lane_stream);
+    if (h->lane_wgrad_stream) cudaStreamDestroy(h->lane_wgrad_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -2263,6 +2269,16 @@ int vaenar_train_step_grads(vaenar_handle_t h, float* params, const void* packed
   if (!getenv("VAENAR_NO_WGRAD_STREAM")) {
     if (!h->wgrad_stream) VB_CUDA(cudaStreamCreateWithFlags(&h->wgrad_stream, cudaStreamNonBlocking));
     c.wstream = h->wgrad_stream;
+  }
+  // decoder forward/backward beside the prior's (not while per-class timing is on: class times must stay exclusive)
+  static const bool no_lane = getenv("VAENAR_NO_DEC_LANE") != nullptr;
+  if (!no_lane && !g_profile) {
+    if (!h->lane_stream) VB_CUDA(cudaStreamCreateWithFlags(&h->lane_stream, cudaStreamNonBlocking));
+    c.lane = h->lane_stream;
+    if (c.wstream) {
+      if (!h->lane_wgrad_stream) VB_CUDA(cudaStreamCreateWithFlags(&h->lane_wgrad_stream, cudaStreamNonBlocking));
+      c.lane_w = h->lane_wgrad_stream;
+    }
   }
   h->ev_cursor = 0;
   train_grads(c, grads, texts, mels, mel_lengths, text_lengths, z_lengths, eps, B, T_text, T_mel, T_z, rf, kl_weight, length_weight,
