@@ -323,6 +323,58 @@ def train_leg(args, world, rank, local, workload, steps, warmup, profile=True):
     return out
 
 
+def mel_inversion_leg(dev, with_cpu):
+    """SURVEY.md 8f rank 4 (audio/utils.py:24-40): the mels of one C2 batch (16 x 870 frames) -> 60 Griffin-Lim
+    iterations -> inverse pre-emphasis -> int16, all on the device (vaenar_tts_b200.audio).  Device time by CUDA events;
+    the CPU figure is the numpy oracle (oracle/audio_oracle.py, the checker) on a bounded sample."""
+    import numpy as np
+    import torch
+    from vaenar_tts_b200 import LJHPS
+    from vaenar_tts_b200.audio import Audio
+    a = Audio(LJHPS.Audio, device=dev)
+    B, T = B_PER_GPU, T_MEL
+    rng = np.random.default_rng(0)
+    tt = np.arange(T)[:, None] / (T - 1)
+    mm = np.arange(80)[None, :] / 80
+    env = np.sin(np.pi * tt) ** 0.5
+    mel = np.clip(0.55 * env * (1 - 0.6 * mm) + 0.15 * np.sin(2 * np.pi * (3 * tt + 2 * mm)) * env
+                  + 0.05 * rng.standard_normal((B, T, 80)), 0, 1).astype(np.float32)
+    d_mel = torch.from_numpy(mel).to(dev)
+    lens = [T] * B
+
+    def run():
+        wav = a.inv_mel_spectrogram_batch(d_mel, lens, seed=1)
+        return a.to_int16_batch(a.inv_preemphasize_batch(wav, lens), lens)
+    run()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = statistics.median(ms) * 1e-3
+    hop, sr, iters = LJHPS.Audio.frame_shift_sample, LJHPS.Audio.sample_rate, LJHPS.Audio.griffin_lim_iters
+    out = {"workload": f"mel inversion of one C2 batch: {B} x {T} frames, {iters} Griffin-Lim iterations (fp64 FFTs), "
+                       "inverse pre-emphasis, int16", "ms_per_batch": t * 1e3,
+           "frames_per_s": B * T / t, "audio_seconds_per_second": B * hop * (T - 1) / sr / t,
+           "launches_per_batch": iters + 7}
+    if with_cpu:
+        from oracle import audio_oracle as AO
+        o = AO.Audio(AO.LJAudio)
+        Tc = 150
+        S = o.linear_magnitudes(mel[0, :Tc].T)
+        r = rng.random(S.shape)
+        t0 = time.perf_counter()
+        o._griffin_lim(S, rand=r, iters=iters)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": Tc / dt, "unit": "frames/s", "kind": "port", "cores": os.cpu_count(),
+                               "sample": f"numpy restatement of audio.py:93-102, 1 utterance x {Tc} frames, {iters} iterations"}
+    return out
+
+
 def run_ours(args):
     import torch
     # ---------------- CPU baseline first (rank 0, before the process group exists: the other ranks simply wait in the
@@ -525,6 +577,8 @@ def run_ours(args):
         tr = train_leg(args, world, rank, local, "c3" if world == 1 else "c4", tsteps, 3, profile=False)
         if rank == 0:
             line["train"] = tr
+    if rank == 0 and world == 1 and not args.no_audio:
+        line["mel_inversion"] = mel_inversion_leg(dev, not args.skip_cpu)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -570,6 +624,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline / eager stand-in legs (profiling runs only)")
     ap.add_argument("--no-train", action="store_true", help="omit the training leg of the default (c2) run")
+    ap.add_argument("--no-audio", action="store_true", help="omit the mel-inversion leg (Griffin-Lim) of the default run at N = 1")
     ap.add_argument("--inflight", type=int, default=3,
                     help="independent batches in flight (own graph, workspace, stream): H2D / compute / D2H of three consecutive "
                          "batches overlap")

@@ -1,5 +1,5 @@
-"""Tiny run of every C-ABI path (inference, call eval, call training-forward, init, two full train_steps) for
-compute-sanitizer."""
+"""Tiny run of every C-ABI path (inference, call eval, call training-forward, init, two full train_steps, mel inversion)
+for compute-sanitizer."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,4 +15,9 @@ out2 = m(inputs=texts, mel_targets=mels, mel_lengths=m_len, text_lengths=t_len, 
 m.init(texts, m_len, t_len)
 for _ in range(2):
     loss = m.train_step(texts, mels, t_len, m_len, 1e-5, 2)
-torch.cuda.synchronize(); print("ok", float(mel.abs().mean()), float(out[2]), float(loss[0]))
+from vaenar_tts_b200.audio import Audio
+a = Audio(LJHPS.Audio, device="cuda")
+lens = [int(x) for x in m_len.clamp(min=2)]
+wav = a.inv_mel_spectrogram_batch(mel.clamp(0, 1), lens, seed=3, iters=3)
+pcm = a.to_int16_batch(a.inv_preemphasize_batch(wav, lens), lens)
+torch.cuda.synchronize(); print("ok", float(mel.abs().mean()), float(out[2]), float(loss[0]), int(pcm.abs().max()))

@@ -131,6 +131,7 @@ struct vaenar_model {
   cudaStream_t wgrad_stream = nullptr;   // weight gradients run beside the activation-gradient chain (train step)
   cudaStream_t lane_stream = nullptr;    // train step: decoder forward + backward run beside the prior's (both hang off z only)
   cudaStream_t lane_wgrad_stream = nullptr;
+  cudaStream_t attn_stream = nullptr, lane_attn_stream = nullptr;   // dK/dV kernels of the attention backward (beside dQ)
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_cursor = 0;
   bool attrs_set = false;
@@ -552,6 +553,8 @@ struct Ctx {
   cudaStream_t wstream = nullptr;        // when set, run_wgrad launches here after an event recorded on `stream`
   cudaStream_t lane = nullptr;           // train step: stream of the decoder branch (null: everything on `stream`)
   cudaStream_t lane_w = nullptr;         // weight-gradient stream of the decoder branch
+  cudaStream_t astream = nullptr;        // when set, the dK/dV kernel of run_attention_bwd launches here (beside dQ)
+  cudaStream_t lane_a = nullptr;         // the decoder branch's
 
   template <typename T>
   T* alloc(int64_t count) {
@@ -959,7 +962,16 @@ struct AttnBwdCall {
   __half* dk; int dk_ld, dk_col0;
   __half* dv; int dv_ld, dv_col0;
 };
-static void run_attention_bwd(Ctx& c, int B, int H, const AttnBwdCall& a) {
+// everything queued on the dK/dV stream so far is ordered before what follows on the main stream
+static void join_attn(Ctx& c) {
+  if (c.dry || !c.astream) return;
+  cudaEvent_t e = next_event(c.m);
+  VB_CUDA(cudaEventRecord(e, c.astream));
+  VB_CUDA(cudaStreamWaitEvent(c.stream, e, 0));
+}
+// dq (main stream) and dk / dv (c.astream when set: the two kernels only share inputs) from dO.  join_dkdv: dk / dv are
+// complete on the main stream when the call returns; otherwise the caller orders its consumers with join_attn().
+static void run_attention_bwd(Ctx& c, int B, int H, const AttnBwdCall& a, bool join_dkdv = true) {
   if (c.dry) return;
   {
     const long rows = static_cast<long>(B) * a.Tq;
@@ -992,9 +1004,15 @@ static void run_attention_bwd(Ctx& c, int B, int H, const AttnBwdCall& a) {
   attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (c.astream) {   // inputs (incl. delta) are final at this point of the main stream
+    cudaEvent_t e = next_event(c.m);
+    VB_CUDA(cudaEventRecord(e, c.stream));
+    VB_CUDA(cudaStreamWaitEvent(c.astream, e, 0));
+    cfg.stream = c.astream;
+  }
   {
     ProfileScope prof(a.causal ? "attn_bwd_dkdv_self" : "attn_bwd_dkdv_cross", 8.0 * work * ATT_D,
-                      static_cast<double>(B) * H * ATT_D * 2 * (2.0 * a.Tq + 4.0 * a.Tk), c.stream);
+                      static_cast<double>(B) * H * ATT_D * 2 * (2.0 * a.Tq + 4.0 * a.Tk), cfg.stream);
     cfg.gridDim = dim3(cdiv(a.Tk, 128), H, B);
     cfg.dynamicSmemBytes = v1 ? ATB_DKDV_SMEM : ATB2_DKDV_SMEM;
     const CUtensorMap tQ64 = make_tmap(a.q, 3, a.q_ld, a.Tq, B, a.q_ld, static_cast<uint64_t>(a.Tq) * a.q_ld, 64, 64);
@@ -1004,6 +1022,7 @@ static void run_attention_bwd(Ctx& c, int B, int H, const AttnBwdCall& a) {
     if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(attn_bwd_dkdv_kernel) failed: %s", cudaGetErrorString(le));
     check_launch("attn_bwd_dkdv_kernel");
   }
+  cfg.stream = c.stream;
   {
     ProfileScope prof(a.causal ? "attn_bwd_dq_self" : "attn_bwd_dq_cross", 6.0 * work * ATT_D,
                       static_cast<double>(B) * H * ATT_D * 2 * (3.0 * a.Tq + 2.0 * a.Tk), c.stream);
@@ -1016,6 +1035,7 @@ static void run_attention_bwd(Ctx& c, int B, int H, const AttnBwdCall& a) {
     if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(attn_bwd_dq_kernel) failed: %s", cudaGetErrorString(le));
     check_launch("attn_bwd_dq_kernel");
   }
+  if (join_dkdv) join_attn(c);
 }
 
 static void run_cast(Ctx& c, const float* in, __half* out, int64_t n) {
@@ -2057,6 +2077,8 @@ int vaenar_destroy(vaenar_handle_t h) {
     if (h->wgrad_stream) cudaStreamDestroy(h->wgrad_stream);
     if (h->lane_stream) cudaStreamDestroy(h->lane_stream);
     if (h->lane_wgrad_stream) cudaStreamDestroy(h->lane_wgrad_stream);
+    if (h->attn_stream) cudaStreamDestroy(h->attn_stream);
+    if (h->lane_attn_stream) cudaStreamDestroy(h->lane_attn_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -2278,6 +2300,15 @@ int vaenar_train_step_grads(vaenar_handle_t h, float* params, const void* packed
     if (c.wstream) {
       if (!h->lane_wgrad_stream) VB_CUDA(cudaStreamCreateWithFlags(&h->lane_wgrad_stream, cudaStreamNonBlocking));
       c.lane_w = h->lane_wgrad_stream;
+    }
+  }
+  static const bool no_attn_stream = getenv("VAENAR_NO_ATTN_STREAM") != nullptr;
+  if (!no_attn_stream && !g_profile) {
+    if (!h->attn_stream) VB_CUDA(cudaStreamCreateWithFlags(&h->attn_stream, cudaStreamNonBlocking));
+    c.astream = h->attn_stream;
+    if (c.lane) {
+      if (!h->lane_attn_stream) VB_CUDA(cudaStreamCreateWithFlags(&h->lane_attn_stream, cudaStreamNonBlocking));
+      c.lane_a = h->lane_attn_stream;
     }
   }
   h->ev_cursor = 0;
