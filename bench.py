@@ -11,9 +11,10 @@ random-init weights.  One "step" = one VAENAR.inference call over one batch of 1
 Prints ONE JSON line (rank 0):
   value        frames/s over exactly K steps with inputs resident in HBM (CUDA-graph replay, CUDA events, L2 flushed
                before the timed region, inputs + weights + workspaces > L2).  `--inflight` independent batches (default
-               3, each with its own graph / workspace / stream) are in flight at a time -- the three-stage serving pipeline
+               4, each with its own graph / workspace / stream) are in flight at a time -- the serving pipeline
                H2D / compute / D2H of consecutive batches; one inference occupies 64 of the 148 SMs for most of its launch
-               chain, so the batches also overlap on the device.  `serial` carries the strictly
+               chain, so the batches also overlap on the device (measured: 2 -> 1.23, 3 -> 1.05, 4 -> 0.985, 5 -> 0.993,
+               6 -> 1.007, 8 -> 1.024 ms per step).  `serial` carries the strictly
                one-step-after-the-other number (latency per step).
   e2e          the same K steps through the public API with pinned-host inputs and pinned-host results inside the timed
                region (H2D + graph + D2H per step), same number of batches in flight; `e2e_with_alignments` also copies
@@ -625,8 +626,8 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline / eager stand-in legs (profiling runs only)")
     ap.add_argument("--no-train", action="store_true", help="omit the training leg of the default (c2) run")
     ap.add_argument("--no-audio", action="store_true", help="omit the mel-inversion leg (Griffin-Lim) of the default run at N = 1")
-    ap.add_argument("--inflight", type=int, default=3,
-                    help="independent batches in flight (own graph, workspace, stream): H2D / compute / D2H of three consecutive "
+    ap.add_argument("--inflight", type=int, default=4,
+                    help="independent batches in flight (own graph, workspace, stream): H2D / compute / D2H of consecutive "
                          "batches overlap")
     ap.add_argument("--train-steps", type=int, default=20, help="timed train steps of the default run's training leg")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],

@@ -131,6 +131,7 @@ struct vaenar_model {
   cudaStream_t wgrad_stream = nullptr;   // weight gradients run beside the activation-gradient chain (train step)
   cudaStream_t lane_stream = nullptr;    // train step: decoder forward + backward run beside the prior's (both hang off z only)
   cudaStream_t lane_wgrad_stream = nullptr;
+  cudaStream_t main_stream = nullptr;    // train step: high-priority stream of the activation chain (forked off the caller's)
   cudaStream_t attn_stream = nullptr, lane_attn_stream = nullptr;   // dK/dV kernels of the attention backward (beside dQ)
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_cursor = 0;
@@ -645,6 +646,13 @@ struct ProfileScope {
   X(128, EPI_LN, 0) X(256, EPI_LN, 0)                                                                \
   X(256, EPI_QKV, F_OUT_H) X(128, EPI_COUPLING, 0) X(256, EPI_POSTERIOR, 0)
 
+// two-CTAs-per-SM instances (GemmCfg<128, 2>): the plain epilogues of the training step's forward / dgrad GEMMs
+#define VB_GEMM_OCC2_INSTANCES(X)                                                                  \
+  X(128, EPI_PLAIN, F_OUT_H) X(128, EPI_PLAIN, F_BIAS | F_RELU | F_OUT_H)                             \
+  X(128, EPI_PLAIN, F_RES | F_OUT_F32) X(128, EPI_PLAIN, F_OUT_F32)                                   \
+  X(128, EPI_PLAIN, F_BIAS | F_RES | F_OUT_F32) X(128, EPI_PLAIN, F_BIAS | F_OUT_F32 | F_OUT_H)
+static int g_gemm_occ2 = 1;   // VAENAR_GEMM_OCC2=0: one CTA per SM everywhere (A/B timing)
+
 static void set_attrs(vaenar_model* m) {
   static bool done = false;
   if (done) return;
@@ -656,6 +664,14 @@ static void set_attrs(vaenar_model* m) {
                                GemmCfg<BN>::kSmemBytes));
   VB_GEMM_INSTANCES(VB_SET_ATTR)
 #undef VB_SET_ATTR
+  if (const char* e = getenv("VAENAR_GEMM_OCC2")) g_gemm_occ2 = atoi(e);
+#define VB_SET_ATTR2(BN, MODE, FEAT)                                                                 \
+  VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, (FEAT), 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               GemmCfg<BN, 2>::kSmemBytes));                                         \
+  VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, (FEAT), 2>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                               cudaSharedmemCarveoutMaxShared));
+  VB_GEMM_OCC2_INSTANCES(VB_SET_ATTR2)
+#undef VB_SET_ATTR2
   VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   VB_CUDA(cudaFuncSetAttribute(attention2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
@@ -667,7 +683,8 @@ static void set_attrs(vaenar_model* m) {
   VB_CUDA(cudaFuncSetAttribute(attn_bwd_dq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB2_DQ_SMEM));
   VB_CUDA(cudaFuncSetAttribute(flow_param_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (2 * FLOW_DIM * (FLOW_DIM + 1) + FLOW_DIM) * 4));
-  VB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+  VB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<128>::kSmem));
+  VB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<256>::kSmem));
   VB_CUDA(cudaFuncSetAttribute(slogdet128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOW_DIM * (FLOW_DIM + 1) * 8));
   VB_CUDA(cudaFuncSetAttribute(inverse128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (FLOW_DIM * (2 * FLOW_DIM + 1) + FLOW_DIM) * 4));
   VB_CUDA(cudaFuncSetAttribute(flow_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOW_LIN_SMEM));
@@ -779,6 +796,18 @@ static void run_gemm(Ctx& c, int block_n, AOp a0, AOp a1, int batches, int rows,
     le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, (FEAT)>, tA0, tA1, tB, p);                       \
     launched = true;                                                                                        \
   }
+  // multi-wave grids of the plain epilogues: two CTAs per SM (the epilogue of one under the mainloop of the other)
+#define VB_TRY2(BN, MODE, FEAT)                                                                             \
+  if (!launched && block_n == BN && p.mode == MODE && feat == static_cast<uint32_t>(FEAT)) {                \
+    cfg.dynamicSmemBytes = GemmCfg<BN, 2>::kSmemBytes;                                                      \
+    le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, (FEAT), 2>, tA0, tA1, tB, p);                    \
+    launched = true;                                                                                        \
+  }
+  if (g_gemm_occ2 && p.mode == EPI_PLAIN && !p.dbg &&
+      static_cast<long>(grid.x) * grid.y > (g_gemm_occ2 > 1 ? 0 : 148)) {
+    VB_GEMM_OCC2_INSTANCES(VB_TRY2)
+  }
+#undef VB_TRY2
   VB_GEMM_INSTANCES(VB_TRY)
   VB_GEMM_INSTANCES(VB_TRY_RT)
 #undef VB_TRY
@@ -826,7 +855,11 @@ static void run_wgrad(Ctx& c, WOp x0, WOp x1, int a_split, WOp dy, int batches, 
   p.batches = batches; p.rows = rows;
   p.kb_per_batch = cdiv(rows, WG_BLOCK_K);
   p.total_kb = batches * p.kb_per_batch;
-  const int tiles = cdiv(M, WG_BLOCK_M) * cdiv(N, WG_BLOCK_N);
+  // 128 x 256 tiles (VAENAR_WGRAD_BN=256; less operand traffic per MMA) measured SLOWER than 128 x 128 at C3 (train step
+  // 11.87 vs 11.74 ms): half as many CTAs per split-K wave outweighs the 25 % smaller fill -- kept for A/B timing only
+  static const int wg_bn_env = getenv("VAENAR_WGRAD_BN") ? atoi(getenv("VAENAR_WGRAD_BN")) : 0;
+  const int bn = (wg_bn_env == 256 && N % 256 == 0) ? 256 : 128;
+  const int tiles = cdiv(M, WG_BLOCK_M) * cdiv(N, bn);
   int splits = std::max(1, std::min(p.total_kb, std::max(1, 148 / tiles)));   // about one wave of CTAs
   p.kb_per_split = cdiv(p.total_kb, splits);
   splits = cdiv(p.total_kb, p.kb_per_split);
@@ -849,9 +882,9 @@ static void run_wgrad(Ctx& c, WOp x0, WOp x1, int a_split, WOp dy, int batches, 
                     c.wstream ? c.wstream : c.stream);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(cdiv(M, WG_BLOCK_M), cdiv(N, WG_BLOCK_N), splits);
+  cfg.gridDim = dim3(cdiv(M, WG_BLOCK_M), cdiv(N, bn), splits);
   cfg.blockDim = dim3(WG_THREADS);
-  cfg.dynamicSmemBytes = WG_SMEM;
+  cfg.dynamicSmemBytes = bn == 256 ? WgCfg<256>::kSmem : WgCfg<128>::kSmem;
   cfg.stream = c.stream;
   if (c.wstream) {   // off the critical path: wait for the producer of dY, then run on the weight-gradient stream
     cudaEvent_t e = next_event(c.m);
@@ -864,7 +897,8 @@ static void run_wgrad(Ctx& c, WOp x0, WOp x1, int a_split, WOp dy, int batches, 
   attr[0].val.programmaticStreamSerializationAllowed = (g_use_pdl && !c.wstream) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, wgrad_tc_kernel, tA0, tA1, tB, p);
+  const cudaError_t le = bn == 256 ? cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<256>, tA0, tA1, tB, p)
+                                   : cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<128>, tA0, tA1, tB, p);
   if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(wgrad_tc_kernel) failed: %s", cudaGetErrorString(le));
   check_launch("wgrad_tc_kernel");
 }
@@ -1095,6 +1129,7 @@ struct MemKV {     // projected memory of all blocks of a module
   __half* k;       // [B*Tt, nblk*d]
   __half* vt;      // [nblk*B*H*64, tpad]
   int nblk, d, tpad;
+  int k_ld = 0;    // row pitch of k when it is a window of a wider tensor (training: K | V row-major), 0: nblk*d
 };
 
 // K/V projections of the text memory for all blocks of a module, one GEMM (attention.py:219-220 hoisted)
@@ -1155,9 +1190,18 @@ struct XTail {
   int cond_off_next = 0;
   const float* pe = nullptr;
 };
+// Training forward: where the fused row kernel leaves the tensors the backward pass reads (XblkTape in train.inc)
+struct XTapeOut {
+  float* o_f = nullptr; __half* o_h = nullptr;   // block output (the input buffers stay intact)
+  float* s_f = nullptr; __half* s_h = nullptr; float* rstd1 = nullptr;
+  __half* q2 = nullptr; float* lse2 = nullptr; __half* ctx2 = nullptr;
+  float* c_f = nullptr; __half* c_h = nullptr; float* rstd2 = nullptr;
+  __half* hid = nullptr; float* rstd3 = nullptr;
+};
+// b.qk: Q | K of the next block, row pitch 2d -- or, with a tape, Q | K | V row-major with pitch 3d
 static void run_xblk_row(Ctx& c, const std::string& pk, const std::string& pn, const std::string& next_pk, Stream2 x,
                          const XblkBufs& b, int B, int T, const int* q_len, const MemKV& kv, int kv_blk, int Tt,
-                         const int* t_len, float* ali, const XTail* tail = nullptr) {
+                         const int* t_len, float* ali, const XTail* tail = nullptr, const XTapeOut* tape = nullptr) {
   if (c.dry) return;
   const int d = XR_D, H = XR_H;
   XRowParams p;
@@ -1176,7 +1220,20 @@ static void run_xblk_row(Ctx& c, const std::string& pk, const std::string& pn, c
   p.x_f = x.f;
   p.has_next = next_pk.empty() ? 0 : 1;
   p.qk_next = b.qk; p.vt_next = b.vt; p.vt_next_ld = b.tpad;
+  p.qk_next_ld = 2 * d;
+  p.x_f_out = x.f;
+  if (tape) {
+    if (tail) VB_THROW("row kernel: the flow tail is an inference-only fusion");
+    p.x_f_out = tape->o_f;
+    p.tp_s_f = tape->s_f; p.tp_s_h = tape->s_h; p.tp_rstd1 = tape->rstd1;
+    p.tp_q2 = tape->q2; p.tp_lse2 = tape->lse2; p.tp_ctx2 = tape->ctx2;
+    p.tp_c_f = tape->c_f; p.tp_c_h = tape->c_h; p.tp_rstd2 = tape->rstd2;
+    p.tp_hid = tape->hid; p.tp_rstd3 = tape->rstd3;
+    if (p.has_next) { p.qk_next_ld = 3 * d; p.v_rm_next = b.qk + 2 * d; }
+  }
   p.ali = ali;
+  static const bool no_n256 = getenv("VAENAR_XR_N128") != nullptr;   // A/B timing: two N = 128 instructions per weight-tile pair
+  p.mma_n256 = no_n256 ? 0 : 1;
   if (tail && tail->coupling) {
     if (tail->pre != !next_pk.empty()) VB_THROW("flow tail: the next q|k|v projection needs the next pre-projection and vice versa");
     p.tail_coupling = 1; p.tail_flow = tail->flow ? 1 : 0; p.tail_pre = tail->pre ? 1 : 0;
@@ -1195,7 +1252,9 @@ static void run_xblk_row(Ctx& c, const std::string& pk, const std::string& pn, c
   const CUtensorMap tX = make_tmap(x.h, 3, d, T, B, d, T64 * d, 64, 128);
   const CUtensorMap tA1 = make_tmap(b.ctx, 3, d, T, B, d, T64 * d, 64, 128);
   const int kld = kv.nblk * kv.d;
-  const CUtensorMap tK = make_tmap(kv.k, 3, kld, Tt, B, kld, static_cast<uint64_t>(Tt) * kld, 64, 128);
+  const int kpitch = kv.k_ld > 0 ? kv.k_ld : kld;
+  const CUtensorMap tK = make_tmap(kv.k, 3, kld, Tt, B, kpitch, static_cast<uint64_t>(Tt) * kpitch, 64, 128);
+  const CUtensorMap tXo = tape ? make_tmap(tape->o_h, 3, d, T, B, d, T64 * d, 64, 128) : tX;
   const CUtensorMap tV = make_tmap(kv.vt, 2, Tt, static_cast<uint64_t>(kv.nblk) * B * H * 64, 1, kv.tpad, 0, 64, 64);
   const CUtensorMap tW1 = make_tmap(c.W(pk + ".proj1"), 2, 2 * d, d, 1, 2 * d, 0, 64, 128);
   const CUtensorMap tWq = make_tmap(c.W(pk + ".cq"), 2, d, d, 1, d, 0, 64, 128);
@@ -1210,9 +1269,10 @@ static void run_xblk_row(Ctx& c, const std::string& pk, const std::string& pn, c
   const double macs_row = 2.0 * d * d + d * d + 2.0 * Tt * d + 2.0 * d * d + 2.0 * d * XR_F + (p.has_next ? 3.0 * d * d : 0.0) +
                           (p.tail_coupling ? 128.0 * d : 0.0) + (p.tail_flow ? 128.0 * 128 : 0.0) + (p.tail_pre ? 64.0 * d : 0.0);
   const double wbytes = 2.0 * (4.0 * d * d + d * d + 2.0 * d * XR_F + (p.has_next ? 3.0 * d * d : 0.0));
-  ProfileScope prof(ali ? "xblk_row_ali" : "xblk_row", 2.0 * rows * macs_row,
+  ProfileScope prof(tape ? "xblk_row_tape" : (ali ? "xblk_row_ali" : "xblk_row"), 2.0 * rows * macs_row,
                     wbytes + rows * d * (4 + 2 + 2 + 4 + 2) + (p.has_next ? rows * 3 * d * 2 : 0) +
-                        static_cast<double>(B) * Tt * 2 * d * 2 + (ali ? rows * H * Tt * 4 : 0),
+                        static_cast<double>(B) * Tt * 2 * d * 2 + (ali ? rows * H * Tt * 4 : 0) +
+                        (tape ? rows * (d * (4 + 2 + 2 + 2 + 4 + 2) + XR_F * 2) : 0),
                     c.stream);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1225,7 +1285,7 @@ static void run_xblk_row(Ctx& c, const std::string& pk, const std::string& pn, c
   attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, xblk_row_kernel, tX, tA1, tK, tV, tW1, tWq, tW2, tF1, tF2, tWn, tWo, tFl, tWp, p);
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, xblk_row_kernel, tX, tA1, tK, tV, tW1, tWq, tW2, tF1, tF2, tWn, tWo, tFl, tWp, tXo, p);
   if (le != cudaSuccess) VB_THROW("cudaLaunchKernelEx(xblk_row_kernel) failed: %s", cudaGetErrorString(le));
   check_launch("xblk_row_kernel");
 }
@@ -2077,6 +2137,7 @@ int vaenar_destroy(vaenar_handle_t h) {
     if (h->wgrad_stream) cudaStreamDestroy(h->wgrad_stream);
     if (h->lane_stream) cudaStreamDestroy(h->lane_stream);
     if (h->lane_wgrad_stream) cudaStreamDestroy(h->lane_wgrad_stream);
+    if (h->main_stream) cudaStreamDestroy(h->main_stream);
     if (h->attn_stream) cudaStreamDestroy(h->attn_stream);
     if (h->lane_attn_stream) cudaStreamDestroy(h->lane_attn_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -2286,6 +2347,23 @@ int vaenar_train_step_grads(vaenar_handle_t h, float* params, const void* packed
   API_BEGIN
   if (!grads || !losses) VB_THROW("null gradient / loss buffer");
   if (!(loss_scale > 0.f)) VB_THROW("loss_scale must be positive");
+  // The activation chain (forward, dgrad chain; the decoder branch) runs on HIGH-priority streams forked off the caller's
+  // stream, the weight-gradient and dK / dV streams keep the default (lowest) priority: the block scheduler then places the
+  // CTAs of the critical chain first and the one-wave weight-gradient grids fill what is left.
+  h->ev_cursor = 0;
+  cudaStream_t user_stream = static_cast<cudaStream_t>(stream);
+  static const bool no_prio = getenv("VAENAR_NO_PRIO") != nullptr;
+  const bool prio = !no_prio && !g_profile;
+  int prio_hi = 0;
+  if (prio) {
+    int prio_lo = 0;
+    VB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    if (!h->main_stream) VB_CUDA(cudaStreamCreateWithPriority(&h->main_stream, cudaStreamNonBlocking, prio_hi));
+    cudaEvent_t e = next_event(h);
+    VB_CUDA(cudaEventRecord(e, user_stream));
+    VB_CUDA(cudaStreamWaitEvent(h->main_stream, e, 0));
+    stream = h->main_stream;
+  }
   Ctx c = make_ctx(h, params, packed, ws, ws_bytes, stream, /*defer_flow_join=*/true);   // joined right before the prior
   apply_train_opts(c, params, opts);
   if (!getenv("VAENAR_NO_WGRAD_STREAM")) {
@@ -2295,7 +2373,7 @@ int vaenar_train_step_grads(vaenar_handle_t h, float* params, const void* packed
   // decoder forward/backward beside the prior's (not while per-class timing is on: class times must stay exclusive)
   static const bool no_lane = getenv("VAENAR_NO_DEC_LANE") != nullptr;
   if (!no_lane && !g_profile) {
-    if (!h->lane_stream) VB_CUDA(cudaStreamCreateWithFlags(&h->lane_stream, cudaStreamNonBlocking));
+    if (!h->lane_stream) VB_CUDA(cudaStreamCreateWithPriority(&h->lane_stream, cudaStreamNonBlocking, prio_hi));
     c.lane = h->lane_stream;
     if (c.wstream) {
       if (!h->lane_wgrad_stream) VB_CUDA(cudaStreamCreateWithFlags(&h->lane_wgrad_stream, cudaStreamNonBlocking));
@@ -2311,9 +2389,13 @@ int vaenar_train_step_grads(vaenar_handle_t h, float* params, const void* packed
       c.lane_a = h->lane_attn_stream;
     }
   }
-  h->ev_cursor = 0;
   train_grads(c, grads, texts, mels, mel_lengths, text_lengths, z_lengths, eps, B, T_text, T_mel, T_z, rf, kl_weight, length_weight,
               loss_scale, losses, mel_out);
+  if (prio) {   // every side stream has been joined into c.stream by train_grads
+    cudaEvent_t e = next_event(h);
+    VB_CUDA(cudaEventRecord(e, c.stream));
+    VB_CUDA(cudaStreamWaitEvent(user_stream, e, 0));
+  }
   API_END
 }
 
@@ -2530,7 +2612,7 @@ int vaenar_griffin_lim(const double* S, const int32_t* n_frames, const double* r
   if (!ws || ws_bytes < need) VB_THROW("griffin_lim: workspace %lld < %lld bytes", (long long)ws_bytes, (long long)need);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static bool attr_set = false;
-  const int smem = sizeof(double2) * (GL_ZSIZE + GL_N / 2);
+  const int smem = GL_SMEM;
   if (!attr_set) {
     VB_CUDA(cudaFuncSetAttribute(gl_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;

@@ -95,14 +95,21 @@ struct GemmParams {
   float* save_lv;                // EPI_POSTERIOR: [M, N/2] log-variance
 };
 
-template <int BLOCK_N>
+// OCC = resident CTAs per SM the instance is built for.  OCC 2 (BLOCK_N 128, EPI_PLAIN without the fp16-lo output): 3
+// pipeline stages (96 KB, which the 8 x 12 KB epilogue slabs fill exactly) and <= 102 registers, so that the epilogue of one
+// CTA (2-5 us of TMEM reads, conversions and stores) runs under the TMA / MMA phase of its neighbour: at d_model 256 the
+// mainloop of a tile is 4-16 k-blocks and the epilogue dominates a one-CTA-per-SM schedule.
+template <int BLOCK_N, int OCC = 1>
 struct GemmCfg {
+  static_assert(OCC == 1 || BLOCK_N == 128, "two CTAs per SM: BLOCK_N 128 only");
   static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N <= 128) ? 6 : (BLOCK_N <= 256 ? 4 : 2);
+  static constexpr int kStages = OCC == 2 ? 3 : ((BLOCK_N <= 128) ? 6 : (BLOCK_N <= 256 ? 4 : 2));
+  static constexpr int kSlabBytes = OCC == 2 ? 3 * 4096 : 4 * 4096;   // per epilogue warp: [res0 | f32 0][res1 | f32 1][f16]([f16-lo])
   static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*cluster LN exchange*/;
+  static constexpr int kSmemBytes =
+      (kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*cluster LN exchange*/ + 1023) / 1024 * 1024;
   static constexpr int kUmmaN = BLOCK_N > 256 ? 256 : BLOCK_N;
   static constexpr int kNumUmmaN = BLOCK_N / kUmmaN;
 };
@@ -120,11 +127,13 @@ __device__ __forceinline__ unsigned long long gtime() {
   return t;
 }
 
-template <int BLOCK_N, int MODE, uint32_t FEAT>
-__global__ void __launch_bounds__(gemm_threads(MODE), 1)
+template <int BLOCK_N, int MODE, uint32_t FEAT, int OCC = 1>
+__global__ void __launch_bounds__(gemm_threads(MODE), OCC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, OCC>;
+  static_assert(OCC == 1 || (MODE == EPI_PLAIN && !(FEAT & (F_OUT_LO | F_RUNTIME))),
+                "two CTAs per SM: plain epilogue with a compile-time feature mask and no fp16-lo output (12 KB slabs)");
   extern __shared__ __align__(1024) uint8_t smem[];   // stays in the shared address space (LDS/STS, not generic)
   if ((smem_u32(smem) & 1023u) != 0) __trap();        // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem_a = smem;
@@ -245,7 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // bank-conflict free.  [res0 | f32 0][res1 | f32 1][f16][f16-lo], 4 KB each: the fp32 output staging
     // aliases the residual slabs (a thread reads its own residual chunk before overwriting it).
     const int half = (warp - 2) >> 2;                // which alternate 64-column chunks this warp handles
-    uint8_t* slab = smem_a + (warp - 2) * (4 * 4096);
+    uint8_t* slab = smem_a + (warp - 2) * Cfg::kSlabBytes;
     uint8_t* s_res = slab;
     uint8_t* s_f32 = slab;
     uint8_t* s_h = slab + 2 * 4096;

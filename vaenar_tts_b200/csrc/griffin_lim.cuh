@@ -44,10 +44,16 @@ __global__ void gl_tables_kernel(double2* __restrict__ tw, double* __restrict__ 
   if (i < win) window[i] = 0.5 - 0.5 * cospi(2.0 * i / win);
 }
 
-// shared-memory index of FFT element p: one pad element per 8 (128 B) so that the strided butterflies of the small
-// stages spread over all banks
-constexpr int GL_ZSIZE = GL_N + GL_N / 8;
-__device__ __forceinline__ int glp(int p) { return p + (p >> 3); }
+// shared-memory index of FFT element / twiddle p (16-byte double2 units; a quarter-warp of 8 lanes is conflict-free when
+// its 8 addresses differ mod 8): one pad element per 8, per 64 and per 512, so that EVERY power-of-two stride -- the
+// butterflies of all stages, the strided twiddle reads tw[i << s] and the bit-reversed accesses of the spectrum
+// separation (stride 256) -- spreads over all banks.  (With the single pad per 8 of the first version 54 % of the kernel's
+// shared-memory wavefronts were bank conflicts: ncu, profiles/griffin_lim_r2.md.)
+__host__ __device__ constexpr int glp(int p) { return p + (p >> 3) + (p >> 6) + (p >> 9); }
+constexpr int GL_ZSIZE = glp(GL_N - 1) + 1;         // 2337
+constexpr int GL_TWSIZE = glp(GL_N / 2 - 1) + 1;    // 1167
+constexpr int GL_SMEM = static_cast<int>(sizeof(double2)) * (GL_ZSIZE + GL_TWSIZE);
+static_assert(2 * GL_TWSIZE >= 2 * GL_MAX_WIN, "the twiddle region also stages the win + hop signal samples of a frame pair");
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -63,9 +69,11 @@ __device__ __forceinline__ void gl_fft_dif(double2* z, const double2* tw) {
   for (int lh = GL_LOGN - 1; lh >= 1; lh -= 2) {          // h = 1024, 256, 64, 16, 4 (stage h and stage h/2 together)
     const int h = 1 << lh, q = h >> 1;
     for (int g = threadIdx.x; g < GL_N / 4; g += GL_THREADS) {
-      const int i = g & (q - 1), blk = g >> (lh - 1);
+      // consecutive lanes take consecutive i (consecutive elements); in the last pass (q = 2) consecutive blocks instead
+      // (elements 8 apart = 9 padded units apart), which keeps the quarter-warps conflict-free there too
+      const int i = q >= 8 ? (g & (q - 1)) : (g >> (GL_LOGN - 1 - lh)), blk = q >= 8 ? (g >> (lh - 1)) : (g & ((GL_N >> (lh + 1)) - 1));
       const int p0 = (blk << (lh + 1)) + i;
-      const double2 w1 = tw[i << (GL_LOGN - 1 - lh)], w2 = tw[i << (GL_LOGN - lh)];
+      const double2 w1 = tw[glp(i << (GL_LOGN - 1 - lh))], w2 = tw[glp(i << (GL_LOGN - lh))];
       const double2 a0 = z[glp(p0)], a1 = z[glp(p0 + q)], a2 = z[glp(p0 + h)], a3 = z[glp(p0 + h + q)];
       const double2 b0 = cadd(a0, a2), b2 = cmul(csub(a0, a2), w1);
       const double2 b1 = cadd(a1, a3), d13 = csub(a1, a3);
@@ -96,9 +104,9 @@ __device__ __forceinline__ void gl_ifft_dit(double2* z, const double2* tw) {
   for (int lh = 1; lh < GL_LOGN; lh += 2) {                      // h = 2, 8, 32, 128, 512 (stage h and stage 2h together)
     const int h = 1 << lh;
     for (int g = threadIdx.x; g < GL_N / 4; g += GL_THREADS) {
-      const int i = g & (h - 1), blk = g >> lh;
+      const int i = h >= 8 ? (g & (h - 1)) : (g >> (GL_LOGN - 2 - lh)), blk = h >= 8 ? (g >> lh) : (g & ((GL_N >> (lh + 2)) - 1));
       const int p0 = (blk << (lh + 2)) + i;
-      const double2 v1 = tw[i << (GL_LOGN - 1 - lh)], v2 = tw[i << (GL_LOGN - 2 - lh)];
+      const double2 v1 = tw[glp(i << (GL_LOGN - 1 - lh))], v2 = tw[glp(i << (GL_LOGN - 2 - lh))];
       const double2 a0 = z[glp(p0)], a1 = z[glp(p0 + h)], a2 = z[glp(p0 + 2 * h)], a3 = z[glp(p0 + 3 * h)];
       const double2 t = cmulc(a1, v1), t2 = cmulc(a3, v1);
       const double2 b0 = cadd(a0, t), b1 = csub(a0, t), b2 = cadd(a2, t2), b3 = csub(a2, t2);
@@ -169,7 +177,9 @@ __device__ __forceinline__ double gl_uniform(unsigned long long seed, unsigned l
 __device__ __forceinline__ double2 gl_unit_phase(double2 a) {      // exp(1j * angle(a)); angle(0) = 0
   double m = sqrt(fma(a.x, a.x, a.y * a.y));
   if (!(m > 1e-140 && m < 1e140)) m = hypot(a.x, a.y);             // squares under/overflowed (or a == 0)
-  return m > 0.0 ? make_double2(a.x / m, a.y / m) : make_double2(1.0, 0.0);
+  if (!(m > 0.0)) return make_double2(1.0, 0.0);
+  const double inv = 1.0 / m;                                      // one division instead of two
+  return make_double2(a.x * inv, a.y * inv);
 }
 
 __global__ void __launch_bounds__(GL_THREADS) gl_iter_kernel(GLParams p) {
@@ -182,11 +192,11 @@ __global__ void __launch_bounds__(GL_THREADS) gl_iter_kernel(GLParams p) {
   if (fa >= nf) return;
   const bool has_b = fb < nf;
   const int tid = threadIdx.x;
-  for (int i = tid; i < GL_N / 2; i += GL_THREADS) tw[i] = p.tw[i];
   const double* Sa = p.S + (static_cast<long>(b) * p.T + fa) * p.s_ld;
   const double* Sb = Sa + p.s_ld;
 
   if (p.first) {
+    for (int i = tid; i < GL_N / 2; i += GL_THREADS) tw[glp(i)] = p.tw[i];
     // angles = exp(2j * pi * rand); y = istft(S * angles): irfft drops the imaginary part of the DC and Nyquist bins
     const long rbase = (static_cast<long>(b) * p.T + fa) * GL_BINS;
     for (int k = tid; k <= GL_N / 2; k += GL_THREADS) {
@@ -209,16 +219,27 @@ __global__ void __launch_bounds__(GL_THREADS) gl_iter_kernel(GLParams p) {
     // stft frames of y = trimmed, reflect-padded overlap-add of the previous iterate
     const double* frames = p.prev + static_cast<long>(b) * p.T * p.win;
     const int L = p.hop * (nf - 1);
+    // The two frames of this CTA overlap by win - hop samples (frame fb at window position m reads the signal sample frame
+    // fa reads at m + hop): every distinct sample is evaluated once (win + hop instead of 2 win overlap-add gathers) and
+    // staged in the twiddle region, which is filled afterwards.
+    double* sig = reinterpret_cast<double*>(tw);
+    const int nsig = has_b ? p.win + p.hop : p.win;
+    for (int u = tid; u < nsig; u += GL_THREADS) {
+      const int mq = u / p.hop, mr = u - mq * p.hop;
+      sig[u] = gl_signal(frames, w, nf, p.win, p.hop, p.lpad, L, fa, u, mq, mr);
+    }
+    __syncthreads();
     for (int n = tid; n < GL_N; n += GL_THREADS) {
       double va = 0.0, vb_ = 0.0;
       const int m = n - p.lpad;
       if (m >= 0 && m < p.win) {
-        const int mq = m / p.hop, mr = m - mq * p.hop;
-        va = w[m] * gl_signal(frames, w, nf, p.win, p.hop, p.lpad, L, fa, m, mq, mr);
-        if (has_b) vb_ = w[m] * gl_signal(frames, w, nf, p.win, p.hop, p.lpad, L, fb, m, mq, mr);
+        va = w[m] * sig[m];
+        if (has_b) vb_ = w[m] * sig[m + p.hop];
       }
       z[glp(n)] = make_double2(va, vb_);
     }
+    __syncthreads();
+    for (int i = tid; i < GL_N / 2; i += GL_THREADS) tw[glp(i)] = p.tw[i];
     __syncthreads();
     gl_fft_dif(z, tw);
     // Z = A + iB with A, B the spectra of the two real frames: A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i

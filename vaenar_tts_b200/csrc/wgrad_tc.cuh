@@ -21,13 +21,18 @@
 namespace vb {
 
 constexpr int WG_BLOCK_M = 128;   // dW rows per CTA (input channels)
-constexpr int WG_BLOCK_N = 128;   // dW cols per CTA (output channels)
 constexpr int WG_BLOCK_K = 64;    // tokens per pipeline stage
-constexpr int WG_STAGES = 6;
 constexpr int WG_THREADS = 192;
 constexpr int WG_CHUNK_BYTES = 64 * WG_BLOCK_K * 2;             // one TMA box: 64 channels x 64 tokens fp16 = 8 KB
-constexpr int WG_STAGE_BYTES = 4 * WG_CHUNK_BYTES;              // A (2 chunks) + B (2 chunks)
-constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+// BN = dW columns per CTA (output channels): 128, or 256 for wide outputs -- a 128 x 256 tile moves 48 KB of operands per
+// 128 x 256 x 64 MMA block instead of 2 x 32 KB (the mainloop is bound by the L2 -> shared-memory fill of one SM, not by
+// the tensor pipe: 25 % tensor-active at 128 x 128, profiles/wgrad_r1.md)
+template <int BN>
+struct WgCfg {
+  static constexpr int kStages = BN == 128 ? 6 : 4;
+  static constexpr int kStageBytes = (2 + BN / 64) * WG_CHUNK_BYTES;   // A (2 chunks) + B (BN / 64 chunks)
+  static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+};
 
 struct WgradParams {
   int batches, rows;       // token geometry [batches][rows]
@@ -61,11 +66,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16_major(uint32_t M, uint32_t
   return (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+template <int BN>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  constexpr int WG_STAGES = WgCfg<BN>::kStages, WG_STAGE_BYTES = WgCfg<BN>::kStageBytes, WG_BLOCK_N = BN;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + WG_STAGES;
@@ -118,8 +125,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           mbar_arrive_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
           tma_load_3d(st, tmA, &full_bar[stage], a_col, t0 + p.a_shift, b);
           tma_load_3d(st + WG_CHUNK_BYTES, tmA, &full_bar[stage], a_col + 64, t0 + p.a_shift, b);
-          tma_load_3d(st + 2 * WG_CHUNK_BYTES, &tmB, &full_bar[stage], p.b_col0 + n0, t0, b);
-          tma_load_3d(st + 3 * WG_CHUNK_BYTES, &tmB, &full_bar[stage], p.b_col0 + n0 + 64, t0, b);
+#pragma unroll
+          for (int cb = 0; cb < WG_BLOCK_N / 64; ++cb)
+            tma_load_3d(st + (2 + cb) * WG_CHUNK_BYTES, &tmB, &full_bar[stage], p.b_col0 + n0 + cb * 64, t0, b);
           if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
         }
       }

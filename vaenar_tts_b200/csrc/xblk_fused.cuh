@@ -87,6 +87,23 @@ struct XRowParams {
   const float* pre_pw;   // [1] pos_weight of the next net
   const float* pe;       // [T, 256] positional-encoding table
   float* ali;            // optional [B, H, T, Tt] fp32 cross-attention alignments
+  int mma_n256;          // 256-wide outputs: one N = 256 MMA per k-step when the two weight tiles sit in adjacent ring slots
+  // ---- training forward: the block output goes to its own buffers and the tensors the backward pass needs are written on
+  // the way (all optional; inference: x_f_out == x_f, the output tensor map == the input one, everything else null)
+  float* x_f_out;        // [B*T, 256] fp32 block output (o_f of the tape)
+  float* tp_s_f;         // LN1 output fp32 / fp16, reciprocal standard deviation
+  __half* tp_s_h;
+  float* tp_rstd1;
+  __half* tp_q2;         // cross-attention queries [B*T, 256]
+  float* tp_lse2;        // [B, H, T] log2 of the cross-attention softmax denominator incl. the maximum
+  __half* tp_ctx2;       // cross-attention context [B*T, 256]
+  float* tp_c_f;         // LN2 output
+  __half* tp_c_h;
+  float* tp_rstd2;
+  __half* tp_hid;        // [B*T, 1024] FFN hidden (post-ReLU)
+  float* tp_rstd3;
+  int qk_next_ld;        // row pitch of qk_next: 512 (Q | K), or 768 when V row-major follows in the same rows (training)
+  __half* v_rm_next;     // training: V of the next block row-major (pitch qk_next_ld), written next to V^T
   unsigned long long* dbg;   // optional per-CTA phase timestamps (tuning aid), 128 x u64 per CTA (globaltimer ns)
 };
 
@@ -97,7 +114,8 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmF1,
                 const __grid_constant__ CUtensorMap tmF2, const __grid_constant__ CUtensorMap tmWn,
                 const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmFl,
-                const __grid_constant__ CUtensorMap tmWp, const __grid_constant__ XRowParams p) {
+                const __grid_constant__ CUtensorMap tmWp, const __grid_constant__ CUtensorMap tmXo,
+                const __grid_constant__ XRowParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* act0 = smem;
@@ -168,6 +186,7 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmWq); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmF1);
     tma_prefetch_desc(&tmF2); tma_prefetch_desc(&tmWn);
     if (p.tail_coupling) { tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmFl); tma_prefetch_desc(&tmWp); }
+    tma_prefetch_desc(&tmXo);
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -291,6 +310,7 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       int f = 0, g = 0;
       const uint32_t R = tmem_base, SCR = tmem_base + 256;
       constexpr uint32_t idesc128 = umma_idesc_f16(128, 128);
+      constexpr uint32_t idesc256 = umma_idesc_f16(128, 256);
       constexpr uint32_t idesc_o = umma_idesc_f16(128, 64);
       const uint32_t a0 = smem_u32(act0), a1 = smem_u32(act1);
       const uint32_t ring_u32 = smem_u32(ring);
@@ -312,8 +332,19 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         release_tile();
       };
       // group of the two column halves of a 256-wide output for one k-panel
+      // When the group's two ring slots are adjacent in shared memory they form ONE [256 x 64] K-major operand (same
+      // 8-row atom stride): one N = 256 instruction per k-step reads A once for both halves -- 12 KB of shared-memory
+      // operand traffic per 128 x 256 x 16 instead of 16 KB (the SS-operand MMA rate is bound by the shared-memory port).
       auto mma_pair_n = [&](uint32_t a_panel, uint32_t d_tmem, bool acc) {
         wait_group();
+        if (p.mma_n256 && (f % XR_NSLOT) + 1 < XR_NSLOT) {
+          const uint64_t ad = umma_desc_sw128(a_panel), bd = umma_desc_sw128(tile_addr());
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc256, (acc || k > 0) ? 1u : 0u);
+          release_tile();
+          release_tile();
+          return;
+        }
         mma_tile(a_panel, d_tmem, acc);
         mma_tile(a_panel, d_tmem + 128, acc);
       };
@@ -542,7 +573,7 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     auto store_x_global = [&](const uint32_t* xu) {
       bar_all();   // all four panels written and fenced
       if (st) {
-        for (int pn = 0; pn < 4; ++pn) tma_store_3d(&tmX, act0 + pn * XR_PANEL, pn * 64, t0, b);
+        for (int pn = 0; pn < 4; ++pn) tma_store_3d(&tmXo, act0 + pn * XR_PANEL, pn * 64, t0, b);
         tma_store_commit();
       }
 #pragma unroll
@@ -557,12 +588,13 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + (lane >> 3), chunk = lane & 7;
           if (row < rows_here)
-            *reinterpret_cast<uint4*>(p.x_f + (grow0 + row) * XR_D + grp * 64 + hh * 32 + chunk * 4) = *sw(row, chunk);
+            *reinterpret_cast<uint4*>(p.x_f_out + (grow0 + row) * XR_D + grp * 64 + hh * 32 + chunk * 4) = *sw(row, chunk);
         }
       }
     };
     // out_mode 0: fp32 result back into R (residual of the next stage); 1: block output -> global; 2: block output stays on chip
-    auto ln_epi = [&](int vi, int out_mode) {
+    const long grow = static_cast<long>(b) * p.T + t;   // this thread's global row (valid when row_ok)
+    auto ln_epi = [&](int vi, int out_mode, float* tape_f, __half* tape_h, float* tape_rstd) {
       const bool final_out = out_mode != 0;
       const float* bias = pvec + vi * XR_D + grp * 64;
       const float* gamma = bias + XR_D;
@@ -602,6 +634,12 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         xs[g * 4 + 3] = (xs[g * 4 + 3] - mean) * rstd * gq.w + bq.w;
       }
       if (vi == 3) estamp(113);
+      if (tape_rstd && grp == 0 && row_ok) tape_rstd[grow] = rstd;
+      if (tape_f && row_ok) {   // 256 contiguous bytes per thread
+        float4* dst = reinterpret_cast<float4*>(tape_f + grow * XR_D + grp * 64);
+#pragma unroll
+        for (int g = 0; g < 16; ++g) dst[g] = make_float4(xs[g * 4 + 0], xs[g * 4 + 1], xs[g * 4 + 2], xs[g * 4 + 3]);
+      }
       if (!final_out) {
         tmem_st32(R + grp * 64, xu);
         tmem_st32(R + grp * 64 + 32, xu + 32);
@@ -616,6 +654,7 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         u.z = pack_half2(xs[g * 8 + 4], xs[g * 8 + 5]);
         u.w = pack_half2(xs[g * 8 + 6], xs[g * 8 + 7]);
         *reinterpret_cast<uint4*>(prow + ((g ^ (r & 7)) << 4)) = u;
+        if (tape_h && row_ok) *reinterpret_cast<uint4*>(tape_h + grow * XR_D + grp * 64 + g * 8) = u;
       }
       if (vi == 3) estamp(115);
       if (!final_out) tmem_wait_st();
@@ -631,7 +670,7 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_wait(r_full, 0);
     tc_fence_after();
     estamp(2);
-    ln_epi(0, 0);
+    ln_epi(0, 0, p.tp_s_f, p.tp_s_h, p.tp_rstd1);
     estamp(3);
 
     // ---- 2. cross-attention queries: scratch -> fp16 -> ACT1 panel (== head) `grp`
@@ -657,6 +696,10 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         u2.w = pack_half2(__uint_as_float(w[g * 8 + 6]), __uint_as_float(w[g * 8 + 7]));
         *reinterpret_cast<uint4*>(prow + ((g ^ (r & 7)) << 4)) = u;
         *reinterpret_cast<uint4*>(prow + (((4 + g) ^ (r & 7)) << 4)) = u2;
+        if (p.tp_q2 && row_ok) {
+          *reinterpret_cast<uint4*>(p.tp_q2 + grow * XR_D + grp * 64 + g * 8) = u;
+          *reinterpret_cast<uint4*>(p.tp_q2 + grow * XR_D + grp * 64 + 32 + g * 8) = u2;
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -722,6 +765,8 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         bar_all();
         if (h == 1) estamp(109);
         l = (sred[512 + r] + sred[640 + r]) + (sred[768 + r] + sred[896 + r]);
+        if (p.tp_lse2 && grp == 0 && row_ok)   // same statistic as attention_tc_kernel writes for the backward pass
+          p.tp_lse2[(static_cast<long>(b) * XR_H + h) * p.T + t] = row_dead ? 0.f : m * sl2 + log2f(l);
         return row_dead ? 0.f : 1.0f / l;
       };
       // P_h (fp16, unnormalised) -> ACT0 panels; alignments of head h (normalised, fp32) -> global
@@ -783,6 +828,10 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         ub.x = pack_half2(f[8], f[9]); ub.y = pack_half2(f[10], f[11]); ub.z = pack_half2(f[12], f[13]); ub.w = pack_half2(f[14], f[15]);
         *reinterpret_cast<uint4*>(prow + (((grp * 2) ^ (r & 7)) << 4)) = ua;
         *reinterpret_cast<uint4*>(prow + (((grp * 2 + 1) ^ (r & 7)) << 4)) = ub;
+        if (p.tp_ctx2 && row_ok) {
+          *reinterpret_cast<uint4*>(p.tp_ctx2 + grow * XR_D + h * 64 + grp * 16) = ua;
+          *reinterpret_cast<uint4*>(p.tp_ctx2 + grow * XR_D + h * 64 + grp * 16 + 8) = ub;
+        }
         fence_proxy_async_smem();
         tc_fence_before();
         warp_arrive(o_done);
@@ -804,7 +853,7 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_wait(r_full, 1);
     tc_fence_after();
     estamp(22);
-    ln_epi(3, 0);
+    ln_epi(3, 0, p.tp_c_f, p.tp_c_h, p.tp_rstd2);
     estamp(23);
 
     // ---- 5. FFN hidden chunks: relu(acc + b1) -> fp16 -> ACT1 buffer (j & 1), two panels of 64 hidden columns
@@ -829,6 +878,7 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         u.z = pack_half2(fmaxf(__uint_as_float(v[g * 8 + 4]) + bb.x, 0.f), fmaxf(__uint_as_float(v[g * 8 + 5]) + bb.y, 0.f));
         u.w = pack_half2(fmaxf(__uint_as_float(v[g * 8 + 6]) + bb.z, 0.f), fmaxf(__uint_as_float(v[g * 8 + 7]) + bb.w, 0.f));
         *reinterpret_cast<uint4*>(prow + ((((grp & 1) * 4 + g) ^ (r & 7)) << 4)) = u;
+        if (p.tp_hid && row_ok) *reinterpret_cast<uint4*>(p.tp_hid + grow * XR_F + j * 128 + grp * 32 + g * 8) = u;
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -840,7 +890,7 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_wait(r_full, 0);
     tc_fence_after();
     estamp(40);
-    ln_epi(6, p.tail_coupling ? 2 : 1);
+    ln_epi(6, p.tail_coupling ? 2 : 1, nullptr, nullptr, p.tp_rstd3);
     estamp(41);
     pdl_launch_dependents();   // late trigger: a parked dependent grid would only block SMs the other launch chain needs
 
@@ -848,7 +898,6 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (p.tail_coupling) {
       // affine coupling (modules/flow.py:223-257): thread (r, grp) owns 16 of the 64 transformed channels and, for the
       // flow map that follows, the matching 16 channels of the conditioning half
-      const long grow = static_cast<long>(b) * p.T + t;
       const int cond_off = 64 - p.zp_off;
       float zp[16], zc[16];
 #pragma unroll
@@ -1005,7 +1054,7 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           for (int it = 0; it < 4; ++it) {
             const int row = it * 8 + (lane >> 2), chunk = lane & 3;
             if (row < rows_here)
-              *reinterpret_cast<uint4*>(p.qk_next + (grow0 + row) * (2 * XR_D) + j * 128 + grp * 32 + chunk * 8) =
+              *reinterpret_cast<uint4*>(p.qk_next + (grow0 + row) * p.qk_next_ld + j * 128 + grp * 32 + chunk * 8) =
                   *reinterpret_cast<const uint4*>(slab + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
           }
         } else if (row_ok) {
@@ -1014,6 +1063,17 @@ xblk_row_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           __half* dst = p.vt_next + (static_cast<long>(b * XR_H + (n0 >> 6)) * 64 + (n0 & 63)) * p.vt_next_ld + t;
 #pragma unroll
           for (int e = 0; e < 32; ++e) dst[static_cast<long>(e) * p.vt_next_ld] = __float2half_rn(__uint_as_float(v[e]));
+          if (p.v_rm_next) {   // training: the backward pass reads V row-major
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 u;
+              u.x = pack_half2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+              u.y = pack_half2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+              u.z = pack_half2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+              u.w = pack_half2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+              *reinterpret_cast<uint4*>(p.v_rm_next + grow * p.qk_next_ld + n0 + g * 8) = u;
+            }
+          }
         }
         estamp(42 + j);
       }
