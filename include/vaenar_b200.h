@@ -252,6 +252,13 @@ int vaenar_xblk_stack_fwd(vaenar_handle_t h, const float* params, const void* pa
                           int T_text, float* alignments, void* stream);
 /* 1 (default): one fused tcgen05 row kernel per CrossAttentionBLK (csrc/xblk_fused.cuh); 0: the per-op launch chain. */
 int vaenar_set_fused(int on);
+/* Training forward of a CrossAttentionBLK (the tape-recording half of train.py:129-134): -1 = automatic (the fused row
+ * kernel with tape outputs when B * ceil(T / 128) >= 96 row tiles, else the per-op launch chain), 0 = per-op chain,
+ * 1 = fused row kernel whenever the shapes allow it.  Both produce the same tape; the parity tests run both. */
+int vaenar_set_train_fused(int mode);
+/* Plain-epilogue GEMM instances built for two resident CTAs per SM (csrc/gemm_tc.cuh, GemmCfg<128, 2>): 1 = for grids deeper
+ * than one wave (default), 0 = never, 2 = always. */
+int vaenar_set_gemm_occ2(int mode);
 
 /* Weight gradient of a Dense / Conv1D layer on tcgen05 with MN-major operands (csrc/wgrad_tc.cuh):
  * dW[tap][Cin (+Cin2)][Cout] = sum_{b,t} [X ; X2][b, t + tap - (taps-1)/2, :]^T dY[b, t, :]  (fp32 out, fp16 operands). */

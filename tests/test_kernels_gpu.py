@@ -33,6 +33,24 @@ def test_dense_plain(M, K, N, block_n):
     assert rel_err(out, ref32) < 3e-3, rel_err(out, ref32)
 
 
+@pytest.mark.parametrize("with_res", [False, True])
+@pytest.mark.parametrize("M,K,N", [(6000, 256, 512), (13920, 1024, 256), (5001, 320, 384)])
+def test_dense_two_ctas_per_sm(M, K, N, with_res):
+    """Grids deeper than one wave (> 148 tiles) of the plain epilogues run the GemmCfg<128, 2> instances: 3 pipeline stages,
+    12 KB epilogue slabs, two CTAs per SM.  Same numerics as the one-CTA-per-SM instances (ragged last row tile, K not a
+    multiple of 64 * stages, N tail)."""
+    import gpu_util as G
+    A, W = gen(M, K, seed=11), gen(K, N, seed=12, scale=1 / math.sqrt(K))
+    b = gen(N, seed=13) if with_res else None
+    res = gen(M, N, seed=14) if with_res else None
+    out = G.dense(A, W, b, residual=res, block_n=128)
+    ref16 = A.half().float() @ W.half().float()
+    if with_res:
+        ref16 = ref16 + b + res
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref16) < 2e-5, rel_err(out, ref16)
+
+
 @pytest.mark.parametrize("split_cluster", [False, True])
 @pytest.mark.parametrize("M,K,N", [(300, 512, 256), (200, 1024, 256), (148, 768, 512), (131, 1024, 512)])
 def test_dense_layernorm(M, K, N, split_cluster):

@@ -93,6 +93,72 @@ def test_gradients_vs_oracle_autograd(case, kl_weight):
     assert not bad, (len(bad), bad[:12], worst)
 
 
+@pytest.mark.parametrize("case", list(CASES))
+def test_gradients_fused_training_forward(case):
+    """The training forward of every CrossAttentionBLK through the fused row kernel with tape outputs (csrc/xblk_fused.cuh; the
+    default only from 96 row tiles up, i.e. not at the golden shapes) forced on: same losses and gradients against oracle
+    autograd, and agreement with the per-op launch chain tensor by tensor (both record the same tape)."""
+    from vaenar_tts_b200 import _lib
+    lib = _lib.load()
+    ohps, g, P = load_case(case)
+    ref_losses, ref = oracle_grads(ohps, g, P, 1e-5)
+    _, ref16 = oracle_grads(ohps, g, P, 1e-5, emulate_fp16=True)
+    m = make_model(ohps, P)
+    try:
+        lib.vaenar_set_train_fused(0)
+        n0 = lib.vaenar_launch_count()
+        losses0, got0 = cuda_grads(m, g, 1e-5)
+        n1 = lib.vaenar_launch_count()
+        lib.vaenar_set_train_fused(1)
+        losses1, got1 = cuda_grads(m, g, 1e-5)
+        n2 = lib.vaenar_launch_count()
+    finally:
+        lib.vaenar_set_train_fused(-1)
+    # 16 blocks x (8 -> 2 launches), minus the first q|k|v projection of every module: the fused path really ran
+    assert (n1 - n0) - (n2 - n1) >= 80, (n1 - n0, n2 - n1)
+    for a, b in zip(losses1, ref_losses):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(b)), (losses1, ref_losses)
+    for a, b in zip(losses1, losses0):
+        assert abs(a - b) <= 5e-4 * max(1.0, abs(b)), (losses1, losses0)
+    bad, worst = compare(got1, ref, ref16)
+    assert not bad, (len(bad), bad[:12], worst)
+    # two fp16-operand implementations of the same graph: they differ by operand-rounding noise only, i.e. per tensor by no
+    # more than the oracle's own fp16-operand deviation allows (same bound as against the oracle)
+    bad01 = []
+    for k, r in got0.items():
+        nb = float(r.double().norm())
+        if nb < 1e-6:
+            continue
+        rb = ref[k].double().reshape(-1)
+        noise = float((ref16[k].double().reshape(-1) - rb).norm()) / max(float(rb.norm()), 1e-30)
+        err = float((got1[k].double() - r.double()).norm()) / nb
+        if err > min(1e-1, max(2e-2, 3.0 * noise)):
+            bad01.append((k, round(err, 5), round(noise, 5)))
+    assert not bad01, bad01[:12]
+
+
+def test_gradients_two_ctas_per_sm_gemms():
+    """Every plain-epilogue GEMM of the step (forward, dgrad, the ReLU-masked dgrad of the FFN) forced through the
+    two-CTAs-per-SM instances, which the default only picks for grids deeper than one wave (C3-sized batches): same losses and
+    gradients against oracle autograd."""
+    from vaenar_tts_b200 import _lib
+    lib = _lib.load()
+    case = list(CASES)[1]
+    ohps, g, P = load_case(case)
+    ref_losses, ref = oracle_grads(ohps, g, P, 1e-5)
+    _, ref16 = oracle_grads(ohps, g, P, 1e-5, emulate_fp16=True)
+    m = make_model(ohps, P)
+    try:
+        lib.vaenar_set_gemm_occ2(2)
+        losses, got = cuda_grads(m, g, 1e-5)
+    finally:
+        lib.vaenar_set_gemm_occ2(1)
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(b)), (losses, ref_losses)
+    bad, worst = compare(got, ref, ref16)
+    assert not bad, (len(bad), bad[:12], worst)
+
+
 def test_train_step_moves_parameters_like_oracle_adam():
     """one full train_step: Keras Adam on the CUDA gradients moves every parameter like Adam on the oracle gradients"""
     case = list(CASES)[0]

@@ -90,6 +90,8 @@ _SIGS = {
     "vaenar_test_wgrad": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P]),
     "vaenar_xblk_stack_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "vaenar_set_fused": (c_int, [c_int]),
+    "vaenar_set_train_fused": (c_int, [c_int]),
+    "vaenar_set_gemm_occ2": (c_int, [c_int]),
     "vaenar_debug_xrow_timestamps": (c_int, [_P]),
     "vaenar_griffin_lim_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "vaenar_mel_to_linear": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_float, _P,

@@ -631,7 +631,7 @@ struct ProfileScope {
 
 #define VB_GEMM_INSTANCES(X)                                                                       \
   X(128, EPI_PLAIN, F_RUNTIME) X(256, EPI_PLAIN, F_RUNTIME)                                          \
-  X(128, EPI_PLAIN, F_OUT_H) X(128, EPI_PLAIN, F_BIAS | F_RELU | F_OUT_H)                             \
+  X(128, EPI_PLAIN, F_OUT_H) X(128, EPI_PLAIN, F_BIAS | F_RELU | F_OUT_H) X(128, EPI_PLAIN, F_MASK | F_OUT_H)  \
   X(128, EPI_PLAIN, F_BIAS | F_TABLE | F_OUT_F32 | F_OUT_H)                                           \
   X(128, EPI_PLAIN, F_BIAS | F_RELU | F_BN | F_OUT_H)                                                 \
   X(128, EPI_PLAIN, F_BIAS | F_TANH | F_BN | F_OUT_H | F_OUT_LO)                                      \
@@ -648,9 +648,10 @@ struct ProfileScope {
 
 // two-CTAs-per-SM instances (GemmCfg<128, 2>): the plain epilogues of the training step's forward / dgrad GEMMs
 #define VB_GEMM_OCC2_INSTANCES(X)                                                                  \
-  X(128, EPI_PLAIN, F_OUT_H) X(128, EPI_PLAIN, F_BIAS | F_RELU | F_OUT_H)                             \
+  X(128, EPI_PLAIN, F_OUT_H) X(128, EPI_PLAIN, F_BIAS | F_RELU | F_OUT_H) X(128, EPI_PLAIN, F_MASK | F_OUT_H)  \
   X(128, EPI_PLAIN, F_RES | F_OUT_F32) X(128, EPI_PLAIN, F_OUT_F32)                                   \
   X(128, EPI_PLAIN, F_BIAS | F_RES | F_OUT_F32) X(128, EPI_PLAIN, F_BIAS | F_OUT_F32 | F_OUT_H)
+static int g_train_fused = -1;   // vaenar_set_train_fused / VAENAR_TRAIN_FUSED: -1 auto, 0 per-op chain, 1 fused row kernel
 static int g_gemm_occ2 = 1;   // VAENAR_GEMM_OCC2=0: one CTA per SM everywhere (A/B timing)
 
 static void set_attrs(vaenar_model* m) {
@@ -782,7 +783,8 @@ static void run_gemm(Ctx& c, int block_n, AOp a0, AOp a1, int batches, int rows,
   if (p.mode == EPI_PLAIN) {
     feat = (p.bias ? F_BIAS : 0) | (p.act == 1 ? F_RELU : 0) | (p.act == 2 ? F_TANH : 0) | (p.ch_scale ? F_BN : 0) |
            (p.add_table ? F_TABLE : 0) | (p.residual ? F_RES : 0) | (p.out_f32 ? F_OUT_F32 : 0) | (p.out_h ? F_OUT_H : 0) |
-           (p.out_lo ? F_OUT_LO : 0);
+           (p.out_lo ? F_OUT_LO : 0) | (p.mask_h ? F_MASK : 0);
+    if (p.mask_h && (p.residual || p.out_f32)) VB_THROW("gemm: the output mask excludes the residual and the fp32 output");
   }
 #define VB_TRY(BN, MODE, FEAT)                                                                              \
   if (!launched && block_n == BN && p.mode == MODE && (MODE != EPI_PLAIN || feat == static_cast<uint32_t>(FEAT))) { \
@@ -2851,6 +2853,21 @@ int vaenar_test_attention(const float* q, const float* k, const float* v, const 
 int vaenar_set_fused(int on) {
   set_attrs(nullptr);
   g_use_fused = on != 0;
+  return 0;
+}
+
+// Plain-epilogue GEMMs: 1 (default) the two-CTAs-per-SM instances for grids deeper than one wave, 0 never, 2 always (parity
+// tests at small shapes).
+int vaenar_set_gemm_occ2(int mode) {
+  set_attrs(nullptr);
+  g_gemm_occ2 = mode;
+  return 0;
+}
+
+// Training forward of a CrossAttentionBLK: -1 (default) fused row kernel when the row tiles fill the chip, 0 per-op chain
+// always, 1 fused row kernel whenever the shapes allow it (parity tests at small shapes).
+int vaenar_set_train_fused(int mode) {
+  g_train_fused = mode < 0 ? -1 : (mode != 0);
   return 0;
 }
 

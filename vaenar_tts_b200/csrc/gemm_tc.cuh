@@ -36,6 +36,7 @@ enum EpiMode : int {
 // Compile-time epilogue feature mask of EPI_PLAIN (F_RUNTIME = decide from the GemmParams pointers at run time)
 enum : uint32_t {
   F_BIAS = 1, F_RELU = 2, F_TANH = 4, F_BN = 8, F_TABLE = 16, F_RES = 32, F_OUT_F32 = 64, F_OUT_H = 128, F_OUT_LO = 256,
+  F_MASK = 512,   // out = acc where mask_h != 0, else 0 (ReLU backward inside the dgrad GEMM); excludes F_RES / F_OUT_F32
   F_RUNTIME = 0x80000000u
 };
 
@@ -66,6 +67,8 @@ struct GemmParams {
   int add_ld;
   const float* residual;         // [M, res_ld] fp32 or null
   int res_ld;
+  const __half* mask_h;          // [M, mask_ld] fp16 or null: outputs are zeroed where the mask element is 0 (post-ReLU activation)
+  int mask_ld;
   const float* ln_gamma;
   const float* ln_beta;
   float ln_eps;
@@ -283,6 +286,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           *reinterpret_cast<uint4*>(g + (grow0 + row) * ld + col0 + chunk * 4) = *sw(base, row, chunk);
       }
     };
+    auto load_f16_slab = [&](uint8_t* base, const __half* g, int ld, int col0, int ncols_valid) {   // [rows_here x 64] fp16
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + (lane >> 3), chunk = lane & 7;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (row < rows_here && chunk * 8 < ncols_valid) u = __ldg(reinterpret_cast<const uint4*>(g + (grow0 + row) * ld + col0 + chunk * 8));
+        *sw(base, row, chunk) = u;
+      }
+    };
     auto store_f16_slab = [&](uint8_t* base, __half* g, int ld, int col0, int ncols_valid) {
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -320,6 +332,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const bool f_f32 = RT ? (p.out_f32 != nullptr) : ((FEAT & F_OUT_F32) != 0);
       const bool f_h = RT ? (p.out_h != nullptr) : ((FEAT & F_OUT_H) != 0);
       const bool f_lo = RT ? (p.out_lo != nullptr) : ((FEAT & F_OUT_LO) != 0);
+      const bool f_mask = RT ? (p.mask_h != nullptr) : ((FEAT & F_MASK) != 0);
+      static_assert(RT || !(FEAT & F_MASK) || !(FEAT & (F_RES | F_OUT_F32)), "the mask tile is staged in the residual / fp32 slab");
       const int act = RT ? p.act : ((FEAT & F_RELU) ? 1 : ((FEAT & F_TANH) ? 2 : 0));
       for (int dc = half; dc < BLOCK_N / 64; dc += 2) {
         const int n0 = n_tile * BLOCK_N + dc * 64;
@@ -330,6 +344,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           load_f32_slab(s_res, p.residual, p.res_ld, n0, nvalid);
           load_f32_slab(s_res + 4096, p.residual, p.res_ld, n0 + 32, nvalid - 32);
         }
+        if (f_mask) load_f16_slab(s_res, p.mask_h, p.mask_ld, n0, nvalid);
         tmem_ld32(taddr + dc * 64, v);
         tmem_ld32(taddr + dc * 64 + 32, w);
         tmem_wait_ld();
@@ -381,6 +396,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const uint4 rq = *sw(s_res + hh * 4096, lane, g);
                 x[0] += __uint_as_float(rq.x); x[1] += __uint_as_float(rq.y);
                 x[2] += __uint_as_float(rq.z); x[3] += __uint_as_float(rq.w);
+              }
+              if (f_mask) {   // 8 mask halves per 16-byte chunk: columns hh * 32 + g * 4 .. + 3 sit in chunk hh * 4 + g / 2
+                const uint4 mq = *sw(s_res, lane, hh * 4 + (g >> 1));
+                const uint32_t m01 = (g & 1) ? mq.z : mq.x, m23 = (g & 1) ? mq.w : mq.y;
+                x[0] = (m01 & 0x7fffu) ? x[0] : 0.f; x[1] = (m01 & 0x7fff0000u) ? x[1] : 0.f;
+                x[2] = (m23 & 0x7fffu) ? x[2] : 0.f; x[3] = (m23 & 0x7fff0000u) ? x[3] : 0.f;
               }
             }
             if (f_f32)
