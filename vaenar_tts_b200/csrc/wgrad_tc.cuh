@@ -14,7 +14,9 @@
 //     the rest from map A1.
 //   * Split-K over token blocks across blockIdx.z; partial tiles are accumulated into the flat gradient
 //     buffer with coalesced fp32 reductions (red.global.add.f32).
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue (two per TMEM lane quadrant, each
+// taking half of the tile's columns; 16-byte vector reductions).  The epilogue was 30-50 % of a CTA's life with four warps
+// and scalar reductions (ncu source view of the round-1 capture): a split-K CTA only has 12-24 token blocks of mainloop.
 #pragma once
 #include "ptx.cuh"
 
@@ -22,7 +24,8 @@ namespace vb {
 
 constexpr int WG_BLOCK_M = 128;   // dW rows per CTA (input channels)
 constexpr int WG_BLOCK_K = 64;    // tokens per pipeline stage
-constexpr int WG_THREADS = 192;
+constexpr int WG_THREADS = 320;
+constexpr int WG_TILE_LD = 36;    // floats per row of the epilogue staging tile (16-byte aligned rows, conflict-free float4 access)
 constexpr int WG_CHUNK_BYTES = 64 * WG_BLOCK_K * 2;             // one TMA box: 64 channels x 64 tokens fp16 = 8 KB
 // BN = dW columns per CTA (output channels): 128, or 256 for wide outputs -- a 128 x 256 tile moves 48 KB of operands per
 // 128 x 256 x 64 MMA block instead of 2 x 32 KB (the mainloop is bound by the L2 -> shared-memory fill of one SM, not by
@@ -60,6 +63,10 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr_bytes,
   d |= 1ull << 46;
   d |= 2ull << 61;
   return d;
+}
+// 16-byte vector reduction into global memory (sm_90+): four fp32 adds, no return value
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 // kind::f16 instruction descriptor with selectable operand majors (bit 15: A MN-major, bit 16: B MN-major)
 __host__ __device__ constexpr uint32_t umma_idesc_f16_major(uint32_t M, uint32_t N, bool a_mn, bool b_mn) {
@@ -156,25 +163,47 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       }
     } else {
       // ===================== epilogue: TMEM -> smem transpose -> coalesced fp32 reductions =====================
-      const int quad = warp & 3;
-      float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);   // pipeline stages are idle by now
+      const int quad = warp & 3;               // TMEM lane quadrant (hardware rule: warp id % 4)
+      const int half = (warp - 2) >> 2;        // column half of the tile this warp reduces
+      float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * WG_TILE_LD);   // pipeline stages are idle by now
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
       uint32_t v[32];
-      for (int c0 = 0; c0 < WG_BLOCK_N; c0 += 32) {
+      // 16-byte reductions need 4-column groups inside one output tensor and 16-byte aligned rows
+      const bool vec_ok = (p.ldo % 4 == 0) && (p.N % 4 == 0) && (p.n_per_out % 4 == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.n_per_out ? p.outs[0] : p.out) & 15) == 0);
+      for (int c0 = half * (WG_BLOCK_N / 2); c0 < (half + 1) * (WG_BLOCK_N / 2); c0 += 32) {
         if (n0 + c0 >= p.N) break;
         __syncwarp();
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 8; ++j)   // lane == row of the tile: eight 16-byte stores, rows 144 B apart
+          *reinterpret_cast<uint4*>(tile + lane * WG_TILE_LD + j * 4) = make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
         __syncwarp();
-        const int col = n0 + c0 + lane;
-        if (col < p.N) {
-          float* dst = p.n_per_out ? p.outs[col / p.n_per_out] + (col % p.n_per_out) : p.out + col;
-          for (int rr = 0; rr < 32; ++rr) {
-            const int row = m0 + quad * 32 + rr;
-            if (row < p.M) atomicAdd(dst + static_cast<long>(row) * p.ldo, tile[rr * 33 + lane]);
+        if (vec_ok) {
+          // lane -> (row it * 4 + lane / 8, columns (lane % 8) * 4 .. + 3): one instruction reduces 4 rows x 128 B
+          const int col = n0 + c0 + (lane & 7) * 4;
+          if (col < p.N) {
+            float* dst = p.n_per_out ? p.outs[col / p.n_per_out] + (col % p.n_per_out) : p.out + col;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3);
+              const int row = m0 + quad * 32 + rr;
+              if (row < p.M) {
+                const float4 q = *reinterpret_cast<const float4*>(tile + rr * WG_TILE_LD + (lane & 7) * 4);
+                red_add_v4(dst + static_cast<long>(row) * p.ldo, q);
+              }
+            }
+          }
+        } else {
+          const int col = n0 + c0 + lane;
+          if (col < p.N) {
+            float* dst = p.n_per_out ? p.outs[col / p.n_per_out] + (col % p.n_per_out) : p.out + col;
+            for (int rr = 0; rr < 32; ++rr) {
+              const int row = m0 + quad * 32 + rr;
+              if (row < p.M) atomicAdd(dst + static_cast<long>(row) * p.ldo, tile[rr * WG_TILE_LD + lane]);
+            }
           }
         }
       }
