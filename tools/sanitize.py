@@ -1,4 +1,4 @@
-"""Tiny run of every C-ABI path (inference, call eval, call training-forward, init, two full train_steps, mel inversion)
+"""Tiny run of every C-ABI path (inference, call eval, call training-forward, init, two full train_steps + one with the fused training forward and the two-CTAs-per-SM GEMMs forced, mel inversion)
 for compute-sanitizer."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -15,6 +15,13 @@ out2 = m(inputs=texts, mel_targets=mels, mel_lengths=m_len, text_lengths=t_len, 
 m.init(texts, m_len, t_len)
 for _ in range(2):
     loss = m.train_step(texts, mels, t_len, m_len, 1e-5, 2)
+# the variants the default only picks at C3-sized batches: training forward through the fused row kernel (tape stores),
+# two-CTAs-per-SM GEMM instances (incl. the ReLU-masked dgrad)
+from vaenar_tts_b200 import _lib
+lib = _lib.load()
+lib.vaenar_set_train_fused(1); lib.vaenar_set_gemm_occ2(2)
+loss = m.train_step(texts, mels, t_len, m_len, 1e-5, 2)
+lib.vaenar_set_train_fused(-1); lib.vaenar_set_gemm_occ2(1)
 from vaenar_tts_b200.audio import Audio
 a = Audio(LJHPS.Audio, device="cuda")
 lens = [int(x) for x in m_len.clamp(min=2)]

@@ -17,6 +17,9 @@ if os.path.exists(path):
     idx = [i for i, r in enumerate(rows) if "embed_kernel" in r["Kernel Name"]]
     # dual-chain inference: the batch is split in two halves that run as two launch chains -> two embed kernels per step
     step = rows[idx[-3]:idx[-1]] if len(idx) >= 3 else rows
+    single_chain = len(idx) >= 2 and (idx[-1] - idx[-2]) <= 100   # round 2: one launch chain of ~75 kernels per step
+    if single_chain:
+        step = rows                                              # the whole -s / -c window (consecutive steps)
     for r in step:
         name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").replace("vb::", "")
         key = (name, r["Grid Size"], r["Block Size"])
@@ -27,10 +30,21 @@ if os.path.exists(path):
         a[1] += v
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(OUT, f"launches_{ROUND}.md"), "w") as f:
-        f.write(f"# ncu launch list, one VAENAR.inference step at C2 (B16, T_text 148, T_mel 870) -- {ROUND}\n\n")
-        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 1`; "
+        if single_chain:
+            per_step = idx[-1] - idx[-2]
+            f.write(f"# ncu launch list, VAENAR.inference at C2 (B16, T_text 148, T_mel 870), one launch chain -- {ROUND}\n\n"
+                    "`ncu --metrics gpu__time_duration.sum --clock-control none -s 90 -c 160 python bench.py --steps 2 --warmup 1 "
+                    "--skip-cpu --no-train --no-audio --inflight 1`\n"
+                    f"(the {len(step)} launches after the warm-up = consecutive steps of {per_step} launches incl. the noise kernel; "
+                    "per-launch times are cold-cache and serialised: compare SHARES).\n\n"
+                    f"{len(step)} launches, {tot:.0f} us summed device time = {tot * per_step / len(step):.0f} us per step serialised.\n\n"
+                    "| kernel | grid | block | launches | total us | avg us | share |\n|---|---|---|---|---|---|---|\n")
+        else:
+          f.write(f"# ncu launch list, one VAENAR.inference step at C2 (B16, T_text 148, T_mel 870) -- {ROUND}\n\n")
+        if not single_chain:
+          f.write("`ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 1`; "
                 "per-launch times are cold-cache and serialised, so compare SHARES, not absolutes.\n\n")
-        f.write(f"{len(step)} launches (both launch chains of the step: batch halves 8 + 8 run concurrently on two streams; ncu "
+          f.write(f"{len(step)} launches (both launch chains of the step: batch halves 8 + 8 run concurrently on two streams; ncu "
                 f"serialises them), {tot:.0f} us summed device time.\n\n| kernel | grid | block | launches | total us | avg us | share |\n|---|---|---|---|---|---|---|\n")
         for (name, grid, blk), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| {name} | {grid} | {blk} | {n} | {t:.1f} | {t / n:.1f} | {t / tot:.3f} |\n")

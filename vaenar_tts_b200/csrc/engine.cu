@@ -862,7 +862,11 @@ static void run_wgrad(Ctx& c, WOp x0, WOp x1, int a_split, WOp dy, int batches, 
   static const int wg_bn_env = getenv("VAENAR_WGRAD_BN") ? atoi(getenv("VAENAR_WGRAD_BN")) : 0;
   const int bn = (wg_bn_env == 256 && N % 256 == 0) ? 256 : 128;
   const int tiles = cdiv(M, WG_BLOCK_M) * cdiv(N, bn);
-  int splits = std::max(1, std::min(p.total_kb, std::max(1, 148 / tiles)));   // about one wave of CTAs
+  // About one wave of CTAs, but at least `min_kb` token blocks per split: the step keeps several streams busy, so what counts
+  // is the SM-time of a launch (CTAs x (prologue + mainloop + reduction epilogue)), not its latency -- a 256 x 256 gradient
+  // cut into 37 splits of 6 token blocks spends most of its SM-time in prologues and atomics.
+  static const int min_kb = getenv("VAENAR_WGRAD_MINKB") ? std::max(1, atoi(getenv("VAENAR_WGRAD_MINKB"))) : 16;
+  int splits = std::max(1, std::min(std::max(1, p.total_kb / min_kb), std::max(1, 148 / tiles)));
   p.kb_per_split = cdiv(p.total_kb, splits);
   splits = cdiv(p.total_kb, p.kb_per_split);
   p.M = M; p.N = N;
