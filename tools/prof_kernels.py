@@ -27,6 +27,15 @@ if which in ("all", "gemm"):
     res = torch.randn(M, 256, generator=g); gm = torch.ones(256); bt = torch.zeros(256)
     for _ in range(2):
         G.dense(A2, W2, b2, residual=res, gamma=gm, beta=bt, ln=True, block_n=256)   # FFN dense2 + residual + LN
+if which in ("all", "gemm2"):
+    # the two most frequent training GEMMs at C3 (13920 rows): grids deeper than one wave -> two-CTAs-per-SM instances
+    M = 32 * Tz
+    A = torch.randn(M, 1024, generator=g); W = torch.randn(1024, 256, generator=g) / 32; res = torch.randn(M, 256, generator=g)
+    for _ in range(2):
+        G.dense(A, W, None, residual=res, block_n=128)                        # dgrad through ffn.dense1, accumulated into g (fp32)
+    A2 = torch.randn(M, 256, generator=g); W2 = torch.randn(256, 1024, generator=g) / 16
+    for _ in range(2):
+        G.dense(A2, W2, None, block_n=128)                                    # K 256 -> N 1024, fp32 out
 if which in ("all", "wgrad"):
     Bw, T = 32, 435                                                                   # C3 token count
     X = torch.randn(Bw, T, 256, generator=g); dY = torch.randn(Bw, T, 1024, generator=g)

@@ -104,11 +104,13 @@ def to_bytes(v, unit):
 
 
 traffic = {}
-KREG = {"attn": "attention_tc", "gemm": "gemm_tc", "wgrad": "wgrad_tc", "attn_bwd": "attn_bwd_d"}
+KREG = {"attn": "attention_tc", "gemm": "gemm_tc", "gemm2": "gemm_tc", "wgrad": "wgrad_tc", "attn_bwd": "attn_bwd_d"}
 for tag, labels in (("attn", ["self-attention causal (B16,H4,Tq=Tk=435)"] * 2 + ["cross-attention (Tq 435, Tk 148)"] * 2 +
                       ["decoder cross-attention with alignments output (Tq 435, Tk 148)"]),
                     ("gemm", ["FFN dense1 + bias + relu (M6960,K256,N1024), BLOCK_N 128"] * 2 +
                      ["FFN dense2 + bias + residual + LayerNorm (M6960,K1024,N256), BLOCK_N 256 single CTA"] * 2),
+                    ("gemm2", ["two CTAs per SM: dgrad through ffn.dense1, accumulated (M13920,K1024,N256), F_RES|F_OUT_F32"] * 2 +
+                     ["two CTAs per SM: (M13920,K256,N1024), fp32 out"] * 2),
                     ("wgrad", ["FFN dense1 weight gradient dW[256,1024] over 13920 tokens (C3)"] * 2 +
                      ["att_proj weight gradient dW[512,256] ([x ; ctx] concat) over 13920 tokens"] * 2),
                     ("attn_bwd", ["causal self-attention backward (B32,H4,T435): dK/dV kernel", "same: dQ kernel"] * 2 +
