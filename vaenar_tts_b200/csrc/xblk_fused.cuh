@@ -19,6 +19,12 @@
 //     memory-K [128 keys x 64], memory-V^T panels [64 x 64 keys]) with TMA.
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2..17 = epilogue / softmax (four column
 //     groups per TMEM lane quadrant, thread == row).
+// Training forward (tape): with the tp_* pointers of XRowParams set, the epilogue warps additionally store -- straight from the
+// registers that already hold them, 64-256 contiguous bytes per thread, no change to the barrier protocol -- every tensor the
+// backward pass of the block reads (LN1 / LN2 outputs fp32 + fp16 and their reciprocal standard deviations, the
+// cross-attention queries, context and log2-sum-exp, the FFN hidden, LN3's reciprocal standard deviation); the block output
+// goes to its own buffers (x_f_out, tensor map tmXo) so that the input survives, and the next block's q | k | v are written
+// row-major with pitch 768 next to V^T.  The flow tail is inference-only.
 // Masking semantics of the reference are kept: fully masked query rows attend uniformly over all T_text keys (their
 // context is the column mean of V, alignments 1/T_text), masked keys of live rows get exactly 0.
 #pragma once
