@@ -17,7 +17,8 @@ algorithm is restated below with numpy:
     float32.
 PARITY UNPINNED against librosa itself (no fixture of the reference exists for this path); the restatement is pinned
 against two independent implementations that are designed to reproduce librosa: ``torch.stft`` / ``torch.istft`` and
-``transformers.audio_utils.mel_filter_bank`` (tests/test_audio_cpu.py).
+``transformers.audio_utils.mel_filter_bank``, and against scipy (a dependency of the reference's audio.py and of librosa:
+``get_window('hann', fftbins=True)``, ``scipy.signal.stft`` framing, ``lfilter``) -- tests/test_audio_cpu.py.
 """
 import numpy as np
 

@@ -82,6 +82,27 @@ def test_inverse_preemphasis_is_the_lfilter_recurrence():
     assert np.abs(A.Audio(A.LJAudio).inv_preemphasize(x) - ref).max() < 1e-12
 
 
+def test_window_and_stft_against_scipy():
+    """scipy is a direct dependency of the reference's audio.py and of librosa 0.8.0: the analysis window is
+    scipy.signal.get_window('hann', win, fftbins=True) (librosa.filters.get_window), and scipy.signal.stft with the same
+    window / hop / reflect boundary yields librosa's frames up to its documented scaling by the window sum."""
+    signal = pytest.importorskip("scipy.signal")
+    for win in (1024, 800, 64):
+        assert np.abs(A.hann_periodic(win) - signal.get_window("hann", win, fftbins=True)).max() < 1e-15
+    audio = A.Audio(A.LJAudio)
+    n_fft, hop, win = audio._stft_parameters()
+    y = np.random.default_rng(9).standard_normal(hop * 17)
+    D = audio._stft(y)
+    w = A.pad_center(A.hann_periodic(win), n_fft)
+    # scipy frames the reflect-padded signal exactly like librosa when nperseg == n_fft (the zero-padded window) and
+    # padded=False; it divides by sum(window)
+    _, _, Z = signal.stft(y, window=w, nperseg=n_fft, noverlap=n_fft - hop, boundary="even", padded=False, return_onesided=True)
+    k = min(Z.shape[1], D.shape[1])
+    assert k >= D.shape[1] - 1
+    # 'even' extension == numpy 'reflect' padding
+    assert np.abs(Z[:, :k] * w.sum() - D[:, :k]).max() < 1e-9 * np.abs(D).max()
+
+
 def test_griffin_lim_reduces_spectral_inconsistency():
     """Each projection step cannot increase || |stft(y)| - S || (Griffin & Lim 1984): a known-answer property."""
     rng = np.random.default_rng(5)
